@@ -32,24 +32,24 @@ class SqliteDirectoryModel:
     def update(self, type_, id_, address):  # sqlite.rs:68-85
         with self.db:
             self.db.execute(
-                "INSERT INTO object_placement(struct_name, object_id, server_address) VALUES (?1, ?2, ?3) "
-                "ON CONFLICT(struct_name, object_id) DO UPDATE SET server_address=?3",
-                (type_, id_, address),
+                "INSERT INTO object_placement(struct_name, object_id, server_address) VALUES (:p1, :p2, :p3) "
+                "ON CONFLICT(struct_name, object_id) DO UPDATE SET server_address=:p3",
+                {"p1": type_, "p2": id_, "p3": address},
             )
 
     def lookup(self, type_, id_):  # sqlite.rs:86-100 (errors are swallowed to None there too)
         row = self.db.execute(
-            "SELECT server_address FROM object_placement WHERE struct_name = ?1 and object_id = ?2",
-            (type_, id_),
+            "SELECT server_address FROM object_placement WHERE struct_name = :p1 and object_id = :p2",
+            {"p1": type_, "p2": id_},
         ).fetchone()
         return None if row is None else row[0]
 
     def clean_server(self, address):  # sqlite.rs:101-112
         with self.db:
-            self.db.execute("DELETE FROM object_placement WHERE server_address = ?1", (address,))
+            self.db.execute("DELETE FROM object_placement WHERE server_address = :p1", {"p1": address})
 
     def remove(self, type_, id_):  # sqlite.rs:114-126
         with self.db:
             self.db.execute(
-                "DELETE FROM object_placement WHERE struct_name = ?1 and object_id = ?2", (type_, id_)
+                "DELETE FROM object_placement WHERE struct_name = :p1 and object_id = :p2", {"p1": type_, "p2": id_}
             )
