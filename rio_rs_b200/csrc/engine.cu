@@ -1,0 +1,1162 @@
+// engine.cu -- host side of librio_cuda: engine state, node-table builds, directory sizing, the bounded-load
+// round protocol, the NCCL counter exchange, and every extern "C" entry point declared in include/rio_cuda.h.
+//
+// Reference interface mirrored: trait ObjectPlacement (rio-rs/src/object_placement/mod.rs:38-56) and the policy
+// around it (rio-rs/src/service.rs:193-254).  There is NO CPU fallback anywhere in this file: without a CUDA
+// device rio_cuda_create fails with RIO_ERR_UPSTREAM.
+#include "../../include/rio_cuda.h"
+#include "kernels.cuh"
+#include "spec.cuh"
+
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+using namespace rio;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct RioError {
+    rio_status code;
+    std::string msg;
+};
+
+#define CUDA_TRY(expr)                                                                                         \
+    do {                                                                                                       \
+        cudaError_t e__ = (expr);                                                                              \
+        if (e__ != cudaSuccess)                                                                                \
+            throw RioError{RIO_ERR_UPSTREAM, std::string(#expr) + ": " + cudaGetErrorString(e__)};             \
+    } while (0)
+#define REQUIRE(cond, msg)                                                      \
+    do {                                                                        \
+        if (!(cond)) throw RioError{RIO_ERR_UNKNOWN, std::string(msg)};         \
+    } while (0)
+
+// ---- NCCL through dlopen: no link-time dependency, and inside a torch process we share torch's libnccl ----
+struct NcclId { char internal[128]; };
+typedef void *NcclComm;
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(NcclId *) = nullptr;
+    int (*CommInitRank)(NcclComm *, int, NcclId, int) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, NcclComm, cudaStream_t) = nullptr;
+    int (*CommDestroy)(NcclComm) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    std::string load_error;
+    bool load() {
+        if (lib) return true;
+        const char *names[] = {getenv("RIO_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char *nm : names) {
+            if (!nm || !*nm) continue;
+            lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+            load_error = dlerror();
+        }
+        if (!lib) return false;
+        GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+        AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
+        CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+        GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !AllGather || !CommDestroy) { load_error = "libnccl lacks required symbols"; lib = nullptr; return false; }
+        return true;
+    }
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+constexpr int kNcclUint32 = 3;
+
+#define NCCL_TRY(expr)                                                                                              \
+    do {                                                                                                            \
+        int r__ = (expr);                                                                                           \
+        if (r__ != 0)                                                                                               \
+            throw RioError{RIO_ERR_UPSTREAM, std::string(#expr) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "nccl error")}; \
+    } while (0)
+
+// ---- growable stream-ordered device buffer ---------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    void ensure(size_t need, cudaStream_t st) {
+        if (need <= bytes) return;
+        size_t nb = std::max(need, bytes + bytes / 2);
+        nb = (nb + 255) & ~(size_t)255;
+        if (p) CUDA_TRY(cudaFreeAsync(p, st));
+        p = nullptr; bytes = 0;
+        CUDA_TRY(cudaMallocAsync(&p, nb, st));
+        bytes = nb;
+    }
+    void release(cudaStream_t st) { if (p) cudaFreeAsync(p, st); p = nullptr; bytes = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct NodeInfo {
+    std::string addr;
+    uint64_t seed = 0, seed2 = 0;
+    uint32_t weight = 0;
+    bool active = false;
+    bool malformed = false;
+    std::vector<float> feat;
+    bool live() const { return active && weight > 0 && !malformed; }
+};
+
+struct TabBufs {
+    DevBuf recs, classes, by_idx;
+    NodeTabDev tab{};
+};
+
+// device scalars (one small allocation): [0]=nsel [1]=moved/removed [2]=new keys (cumulative) [3]=placed ; u32 error at [8]
+enum { S_NSEL = 0, S_MOVED = 1, S_NEWKEYS = 2, S_PLACED = 3, S_COUNT = 8 };
+
+}  // namespace
+
+struct rio_placement {
+    std::mutex mu;
+    int device = 0, sm_count = 0;
+    size_t hbm = 0;
+    std::string devname;
+    cudaStream_t stream = nullptr, h2d_stream = nullptr, d2h_stream = nullptr;
+    uint64_t launches = 0;
+
+    std::vector<NodeInfo> nodes;
+    std::unordered_map<std::string, uint32_t> node_index;
+    uint32_t K = 0;
+    bool tab_dirty = true;
+    TabBufs tabs, tabs_masked;
+    DevBuf d_node_state, d_live, d_fnode;
+
+    DirDev dir{};
+    uint64_t dir_cap = 0;
+    uint64_t dir_keys = 0;      // distinct keys claimed (exact after every host-synchronous call)
+    uint64_t dir_keys_pending = 0;  // pessimistic additions from _dev upserts not yet reconciled
+
+    DevBuf s_keys, s_idx, s_idx2, s_sel, s_slots, s_keys2, s_feats, s_packed, s_offsets, s_cost, s_misc, s_flush, s_gather;
+    unsigned long long *d_scalars = nullptr;   // S_COUNT u64 + error u32
+    unsigned long long *h_scalars = nullptr;   // pinned mirror
+
+    cudaEvent_t events[RIO_MAX_EVENTS] = {};
+    cudaEvent_t ev_pipe[8] = {};
+
+    NcclComm comm = nullptr;
+    int rank = 0, world = 1;
+
+    Launch L() { return Launch{stream, sm_count, &launches}; }
+    uint32_t *d_error() { return reinterpret_cast<uint32_t *>(d_scalars + S_COUNT); }
+};
+
+struct rio_objset {
+    rio_placement *h = nullptr;
+    uint64_t capacity = 0, n = 0;
+    DevBuf keys, idx, feats, counters, sel;
+    uint32_t K = 0;
+    uint32_t counters_n = 0;
+    bool assigned = false;
+};
+
+namespace {
+
+void use_device(rio_placement *h) { CUDA_TRY(cudaSetDevice(h->device)); }
+
+void zero_scalar(rio_placement *h, int which) { CUDA_TRY(cudaMemsetAsync(h->d_scalars + which, 0, 8, h->stream)); }
+uint64_t read_scalar(rio_placement *h, int which) {
+    CUDA_TRY(cudaMemcpyAsync(h->h_scalars + which, h->d_scalars + which, 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return h->h_scalars[which];
+}
+void check_device_error(rio_placement *h) {
+    uint32_t e = 0;
+    CUDA_TRY(cudaMemcpyAsync(&e, h->d_error(), 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (e) { CUDA_TRY(cudaMemsetAsync(h->d_error(), 0, 4, h->stream)); throw RioError{RIO_ERR_UNKNOWN, "directory table overflow (internal sizing error)"}; }
+}
+
+bool address_malformed(const std::string &a) {
+    // service.rs:205-213: splitn(2, ":") must give a non-empty ip and a non-empty port
+    size_t c = a.find(':');
+    return c == std::string::npos || c == 0 || c + 1 >= a.size();
+}
+
+uint32_t intern_node(rio_placement *h, const std::string &addr) {
+    auto it = h->node_index.find(addr);
+    if (it != h->node_index.end()) return it->second;
+    REQUIRE(h->nodes.size() < 0xFFFFFFF0u, "too many nodes");
+    NodeInfo ni;
+    ni.addr = addr;
+    ni.seed = mix64(fnv1a64(addr.data(), addr.size()));
+    ni.seed2 = mix64(ni.seed ^ kSaltNode2);
+    ni.malformed = address_malformed(addr);
+    uint32_t idx = (uint32_t)h->nodes.size();
+    h->nodes.push_back(std::move(ni));
+    h->node_index.emplace(addr, idx);
+    h->tab_dirty = true;
+    return idx;
+}
+
+// Build the class-sorted table of live nodes (optionally excluding `closed`) and upload it.
+void build_tab(rio_placement *h, TabBufs &tb, const std::vector<uint8_t> *closed) {
+    const uint32_t n_total = (uint32_t)h->nodes.size();
+    struct Ent { uint32_t invw, idx; };
+    std::vector<Ent> live;
+    for (uint32_t j = 0; j < n_total; j++) {
+        const NodeInfo &ni = h->nodes[j];
+        if (!ni.live()) continue;
+        if (closed && (*closed)[j]) continue;
+        live.push_back(Ent{inv_weight(ni.weight), j});
+    }
+    std::sort(live.begin(), live.end(), [](const Ent &a, const Ent &b) { return a.invw != b.invw ? a.invw < b.invw : a.idx < b.idx; });
+    std::vector<NodeRec> recs(live.size() ? live.size() : 1);
+    std::vector<ClassRec> classes;
+    for (size_t q = 0; q < live.size(); q++) {
+        const NodeInfo &ni = h->nodes[live[q].idx];
+        recs[q] = NodeRec{(uint32_t)ni.seed, live[q].idx, (uint32_t)ni.seed2, (uint32_t)(ni.seed2 >> 32)};
+        if (q == 0 || live[q].invw != live[q - 1].invw) classes.push_back(ClassRec{(uint32_t)q, live[q].invw});
+    }
+    const uint32_t n_classes = (uint32_t)classes.size();
+    classes.push_back(ClassRec{(uint32_t)live.size(), 0});
+    classes.push_back(ClassRec{(uint32_t)live.size(), 0});   // one spare so classes[c+1] is always readable
+    std::vector<uint4> by_idx(n_total ? n_total : 1);
+    for (uint32_t j = 0; j < n_total; j++) {
+        const NodeInfo &ni = h->nodes[j];
+        const bool lv = ni.live() && !(closed && (*closed)[j]);
+        by_idx[j] = make_uint4((uint32_t)ni.seed, lv ? inv_weight(ni.weight) : 0u, (uint32_t)ni.seed2, (uint32_t)(ni.seed2 >> 32));
+    }
+    cudaStream_t st = h->stream;
+    tb.recs.ensure(recs.size() * sizeof(NodeRec), st);
+    tb.classes.ensure(classes.size() * sizeof(ClassRec), st);
+    tb.by_idx.ensure(by_idx.size() * sizeof(uint4), st);
+    CUDA_TRY(cudaMemcpyAsync(tb.recs.p, recs.data(), recs.size() * sizeof(NodeRec), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(tb.classes.p, classes.data(), classes.size() * sizeof(ClassRec), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(tb.by_idx.p, by_idx.data(), by_idx.size() * sizeof(uint4), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));   // host vectors go out of scope
+    tb.tab.recs = tb.recs.as<NodeRec>();
+    tb.tab.classes = tb.classes.as<ClassRec>();
+    tb.tab.by_idx = tb.by_idx.as<uint4>();
+    tb.tab.n_live = (uint32_t)live.size();
+    tb.tab.n_classes = n_classes;
+    tb.tab.n_total = n_total;
+}
+
+void ensure_tab(rio_placement *h) {
+    if (!h->tab_dirty) return;
+    build_tab(h, h->tabs, nullptr);
+    const uint32_t n_total = (uint32_t)h->nodes.size();
+    std::vector<uint8_t> state(n_total ? n_total : 1, 0);
+    std::vector<uint32_t> live(n_total ? n_total : 1, 0);
+    std::vector<float> fnode((size_t)(n_total ? n_total : 1) * (h->K ? h->K : 1), 0.f);
+    for (uint32_t j = 0; j < n_total; j++) {
+        const NodeInfo &ni = h->nodes[j];
+        state[j] = (ni.live() ? kNodeLive : 0) | (ni.malformed ? kNodeMalformed : 0);
+        live[j] = ni.live() ? 1u : 0u;
+        if (h->K && ni.feat.size() == h->K) std::copy(ni.feat.begin(), ni.feat.end(), fnode.begin() + (size_t)j * h->K);   // others keep zeros
+    }
+    cudaStream_t st = h->stream;
+    h->d_node_state.ensure(state.size(), st);
+    h->d_live.ensure(live.size() * 4, st);
+    h->d_fnode.ensure(fnode.size() * 4, st);
+    CUDA_TRY(cudaMemcpyAsync(h->d_node_state.p, state.data(), state.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->d_live.p, live.data(), live.size() * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->d_fnode.p, fnode.data(), fnode.size() * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    h->tab_dirty = false;
+}
+
+// ---- directory sizing ---------------------------------------------------------------------------------------
+uint64_t pow2_at_least(uint64_t v) { uint64_t p = 1; while (p < v) p <<= 1; return p; }
+
+void dir_alloc(rio_placement *h, uint64_t cap, DirDev &out) {
+    void *p = nullptr;
+    CUDA_TRY(cudaMallocAsync(&p, cap * sizeof(DirSlot), h->stream));
+    out.slots = reinterpret_cast<DirSlot *>(p);
+    out.mask = cap - 1;
+    uint32_t lg = 0; while ((1ull << lg) < cap) lg++;
+    out.shift = 64 - lg;
+    launch_dir_init(h->L(), out.slots, cap);
+}
+
+void reconcile_dir_keys(rio_placement *h) {
+    h->dir_keys = read_scalar(h, S_NEWKEYS);
+    h->dir_keys_pending = 0;
+}
+
+// make room for n_more distinct new keys at load factor <= 0.5 after growth, <= 0.7 before
+void dir_reserve(rio_placement *h, uint64_t n_more) {
+    const uint64_t need = h->dir_keys + h->dir_keys_pending + n_more;
+    if (need * 10 <= h->dir_cap * 7) return;
+    if (h->dir_keys_pending) { reconcile_dir_keys(h); if ((h->dir_keys + n_more) * 10 <= h->dir_cap * 7) return; }
+    const uint64_t new_cap = pow2_at_least(std::max<uint64_t>((h->dir_keys + n_more) * 2, 1024));
+    DirDev nd{};
+    dir_alloc(h, new_cap, nd);
+    CUDA_TRY(cudaMemsetAsync(h->d_scalars + S_NEWKEYS, 0, 8, h->stream));
+    launch_dir_rehash(h->L(), h->dir, nd, h->d_scalars + S_NEWKEYS, h->d_error());
+    CUDA_TRY(cudaFreeAsync(h->dir.slots, h->stream));
+    h->dir = nd;
+    h->dir_cap = new_cap;
+    check_device_error(h);
+    reconcile_dir_keys(h);   // unplaced keys were dropped by the rehash
+}
+
+void dir_upsert_dev(rio_placement *h, const uint64_t *d_keys, const uint32_t *d_idx, uint32_t const_idx, uint64_t n) {
+    if (!n) return;
+    h->s_slots.ensure(n * 8, h->stream);
+    launch_dir_upsert(h->L(), h->dir, d_keys, d_idx, const_idx, n, h->s_slots.as<uint64_t>(), h->d_scalars + S_NEWKEYS, h->d_error());
+}
+
+// ---- counter exchange: the single collective of the path (all-gather of M u32 per rank, then a sum) -------------
+void exchange_counters(rio_placement *h, const uint32_t *d_local, uint32_t *d_global, uint32_t M) {
+    if (h->world <= 1 || !h->comm) {
+        if (d_local != d_global) CUDA_TRY(cudaMemcpyAsync(d_global, d_local, (size_t)M * 4, cudaMemcpyDeviceToDevice, h->stream));
+        return;
+    }
+    h->s_gather.ensure((size_t)M * 4 * h->world, h->stream);
+    NCCL_TRY(g_nccl.AllGather(d_local, h->s_gather.p, M, kNcclUint32, h->comm, h->stream));
+    launch_sum_gathered(h->L(), h->s_gather.as<uint32_t>(), (uint32_t)h->world, M, d_global);
+}
+
+uint32_t capacity_of(uint64_t n_total, uint32_t w, uint64_t w_sum, uint32_t num, uint32_t den) {
+    if (!w || !w_sum || !den) return 0;
+    unsigned __int128 a = (unsigned __int128)num * n_total * w, b = (unsigned __int128)den * w_sum;
+    unsigned __int128 q = (a + b - 1) / b;
+    return q > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)q;
+}
+
+// host keys -> device, chunk-pipelined on three streams so H2D, the score grid and D2H overlap (e2e path)
+void assign_host_pipelined(rio_placement *h, const uint64_t *keys, const float *feats, size_t n, uint32_t *out) {
+    ensure_tab(h);
+    if (feats) REQUIRE(h->K > 0, "assign with object features needs node features (set_nodes feats)");
+    const size_t chunk = 1u << 20;
+    h->s_keys.ensure(n * 8, h->stream);
+    h->s_idx.ensure(n * 4, h->stream);
+    if (feats) h->s_feats.ensure(n * (size_t)h->K * 4, h->stream);
+    CUDA_TRY(cudaEventRecord(h->ev_pipe[0], h->stream));          // buffers (re)allocated on the main stream
+    CUDA_TRY(cudaStreamWaitEvent(h->h2d_stream, h->ev_pipe[0], 0));
+    CUDA_TRY(cudaStreamWaitEvent(h->d2h_stream, h->ev_pipe[0], 0));
+    for (size_t lo = 0; lo < n; lo += chunk) {
+        const size_t m = std::min(chunk, n - lo);
+        CUDA_TRY(cudaMemcpyAsync(h->s_keys.as<uint64_t>() + lo, keys + lo, m * 8, cudaMemcpyHostToDevice, h->h2d_stream));
+        if (feats) CUDA_TRY(cudaMemcpyAsync(h->s_feats.as<float>() + lo * h->K, feats + lo * h->K, m * (size_t)h->K * 4, cudaMemcpyHostToDevice, h->h2d_stream));
+        CUDA_TRY(cudaEventRecord(h->ev_pipe[1], h->h2d_stream));
+        CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_pipe[1], 0));
+        if (feats)
+            launch_assign_affinity(h->L(), h->s_feats.as<float>() + lo * h->K, m, h->d_fnode.as<float>(), h->d_live.as<uint32_t>(), h->tabs.tab.n_total, h->K,
+                                   h->s_idx.as<uint32_t>() + lo, nullptr, nullptr);
+        else
+            launch_assign_hrw(h->L(), h->s_keys.as<uint64_t>() + lo, m, h->tabs.tab, h->s_idx.as<uint32_t>() + lo, nullptr, nullptr, 0);
+        CUDA_TRY(cudaEventRecord(h->ev_pipe[2], h->stream));
+        CUDA_TRY(cudaStreamWaitEvent(h->d2h_stream, h->ev_pipe[2], 0));
+        CUDA_TRY(cudaMemcpyAsync(out + lo, h->s_idx.as<uint32_t>() + lo, m * 4, cudaMemcpyDeviceToHost, h->d2h_stream));
+    }
+    CUDA_TRY(cudaEventRecord(h->ev_pipe[3], h->d2h_stream));
+    CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_pipe[3], 0));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+}
+
+template <class F>
+rio_status guarded(rio_placement *h, F &&f) {
+    try {
+        if (h) {
+            std::lock_guard<std::mutex> g(h->mu);
+            use_device(h);
+            f();
+        } else {
+            f();
+        }
+        return RIO_OK;
+    } catch (const RioError &e) {
+        g_last_error = e.msg;
+        return e.code;
+    } catch (const std::exception &e) {
+        g_last_error = e.what();
+        return RIO_ERR_UNKNOWN;
+    } catch (...) {
+        g_last_error = "unknown C++ exception";
+        return RIO_ERR_UNKNOWN;
+    }
+}
+
+void set_ensure_counters(rio_objset *s) {
+    rio_placement *h = s->h;
+    const uint32_t n_total = (uint32_t)h->nodes.size();
+    if (s->counters_n != n_total || !s->counters.p) {
+        DevBuf nb;
+        nb.ensure((size_t)(n_total ? n_total : 1) * 4, h->stream);
+        CUDA_TRY(cudaMemsetAsync(nb.p, 0, nb.bytes, h->stream));
+        if (s->counters.p && s->counters_n)
+            CUDA_TRY(cudaMemcpyAsync(nb.p, s->counters.p, (size_t)std::min(s->counters_n, n_total) * 4, cudaMemcpyDeviceToDevice, h->stream));
+        s->counters.release(h->stream);
+        s->counters = nb;
+        s->counters_n = n_total;
+    }
+}
+
+}  // namespace
+
+// =====================================================================================================================
+extern "C" {
+
+uint32_t rio_cuda_abi_version(void) { return RIO_ABI_VERSION; }
+
+const char *rio_cuda_last_error(rio_placement *) { return g_last_error.c_str(); }
+
+rio_status rio_cuda_create(const rio_config *cfg, rio_placement **out) {
+    if (!out) { g_last_error = "out is NULL"; return RIO_ERR_UNKNOWN; }
+    *out = nullptr;
+    rio_placement *h = nullptr;
+    try {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            throw RioError{RIO_ERR_UPSTREAM, std::string("no CUDA device available (") + cudaGetErrorString(e) + "); librio_cuda has no CPU fallback"};
+        h = new rio_placement();
+        int dev = cfg && cfg->struct_size >= sizeof(rio_config) ? cfg->device : -1;
+        if (dev < 0) CUDA_TRY(cudaGetDevice(&dev));
+        REQUIRE(dev < ndev, "device ordinal out of range");
+        h->device = dev;
+        CUDA_TRY(cudaSetDevice(dev));
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+        h->sm_count = prop.multiProcessorCount;
+        h->hbm = prop.totalGlobalMem;
+        h->devname = prop.name;
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+        for (auto &ev : h->events) CUDA_TRY(cudaEventCreate(&ev));
+        for (auto &ev : h->ev_pipe) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        // keep freed blocks in the pool: the scratch buffers are re-used every call
+        cudaMemPool_t pool;
+        CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
+        uint64_t thresh = ~0ull;
+        CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+        void *sc = nullptr;
+        CUDA_TRY(cudaMalloc(&sc, (S_COUNT + 1) * 8));
+        CUDA_TRY(cudaMemset(sc, 0, (S_COUNT + 1) * 8));
+        h->d_scalars = reinterpret_cast<unsigned long long *>(sc);
+        CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&h->h_scalars), (S_COUNT + 1) * 8));
+        uint64_t cap = cfg && cfg->struct_size >= sizeof(rio_config) && cfg->directory_capacity ? cfg->directory_capacity : (1ull << 16);
+        cap = pow2_at_least(std::max<uint64_t>(cap, 1024));
+        dir_alloc(h, cap, h->dir);
+        h->dir_cap = cap;
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        *out = h;
+        return RIO_OK;
+    } catch (const RioError &e) {
+        g_last_error = e.msg;
+        delete h;
+        return e.code;
+    } catch (...) {
+        g_last_error = "unknown error in rio_cuda_create";
+        delete h;
+        return RIO_ERR_UNKNOWN;
+    }
+}
+
+void rio_cuda_destroy(rio_placement *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    DevBuf *bufs[] = {&h->tabs.recs, &h->tabs.classes, &h->tabs.by_idx, &h->tabs_masked.recs, &h->tabs_masked.classes, &h->tabs_masked.by_idx,
+                      &h->d_node_state, &h->d_live, &h->d_fnode, &h->s_keys, &h->s_idx, &h->s_idx2, &h->s_sel, &h->s_slots, &h->s_keys2, &h->s_feats,
+                      &h->s_packed, &h->s_offsets, &h->s_cost, &h->s_misc, &h->s_flush, &h->s_gather};
+    for (DevBuf *b : bufs) b->release(h->stream);
+    if (h->dir.slots) cudaFreeAsync(h->dir.slots, h->stream);
+    cudaStreamSynchronize(h->stream);
+    if (h->d_scalars) cudaFree(h->d_scalars);
+    if (h->h_scalars) cudaFreeHost(h->h_scalars);
+    for (auto &ev : h->events) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : h->ev_pipe) if (ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(h->stream);
+    cudaStreamDestroy(h->h2d_stream);
+    cudaStreamDestroy(h->d2h_stream);
+    delete h;
+}
+
+rio_status rio_cuda_sync(rio_placement *h) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] { CUDA_TRY(cudaStreamSynchronize(h->stream)); if (h->dir_keys_pending) reconcile_dir_keys(h); check_device_error(h); });
+}
+
+rio_status rio_cuda_device_info(rio_placement *h, int32_t *device, int32_t *sm_count, uint64_t *hbm_bytes, char *name_buf, size_t name_cap) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] {
+        if (device) *device = h->device;
+        if (sm_count) *sm_count = h->sm_count;
+        if (hbm_bytes) *hbm_bytes = h->hbm;
+        if (name_buf && name_cap) { size_t n = std::min(name_cap - 1, h->devname.size()); memcpy(name_buf, h->devname.data(), n); name_buf[n] = 0; }
+    });
+}
+
+uint64_t rio_cuda_object_key(const char *type, size_t type_len, const char *id, size_t id_len) {
+    uint64_t hsh = fnv1a64(type, type_len);
+    const char dot = '.';
+    hsh = fnv1a64(&dot, 1, hsh);
+    hsh = fnv1a64(id, id_len, hsh);
+    return mix64(hsh);
+}
+
+uint64_t rio_cuda_node_seed(const char *address, size_t len) { return mix64(fnv1a64(address, len)); }
+
+rio_status rio_cuda_hash_ids(rio_placement *h, const char *packed, const uint64_t *offsets, size_t n, uint64_t *out_keys) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] {
+        if (!n) return;
+        REQUIRE(packed && offsets && out_keys, "null buffer");
+        const uint64_t total = offsets[n];
+        h->s_packed.ensure(total + 64, h->stream);
+        h->s_offsets.ensure((n + 1) * 8, h->stream);
+        h->s_keys.ensure(n * 8, h->stream);
+        CUDA_TRY(cudaMemcpyAsync(h->s_packed.p, packed, total, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(h->s_offsets.p, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+        launch_hash_ids(h->L(), h->s_packed.as<char>(), h->s_offsets.as<uint64_t>(), n, h->s_keys.as<uint64_t>());
+        CUDA_TRY(cudaMemcpyAsync(out_keys, h->s_keys.p, n * 8, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    });
+}
+
+// ---- node table ----------------------------------------------------------------------------------------------------
+rio_status rio_cuda_set_nodes(rio_placement *h, const char *const *addrs, const uint32_t *weights, const float *feats, uint32_t M, uint32_t K,
+                              uint32_t *out_idx) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] {
+        REQUIRE(M == 0 || addrs, "addrs is NULL");
+        REQUIRE(!feats || K > 0, "feats given with K == 0");
+        if (feats) { h->K = K; for (auto &ni : h->nodes) ni.feat.clear(); }
+        for (auto &ni : h->nodes) ni.active = false;
+        for (uint32_t j = 0; j < M; j++) {
+            REQUIRE(addrs[j], "null address");
+            const uint32_t idx = intern_node(h, addrs[j]);
+            NodeInfo &ni = h->nodes[idx];
+            ni.weight = weights ? weights[j] : 1u;
+            ni.active = true;
+            if (feats) ni.feat.assign(feats + (size_t)j * K, feats + (size_t)(j + 1) * K);
+            if (out_idx) out_idx[j] = idx;
+        }
+        h->tab_dirty = true;
+    });
+}
+
+rio_status rio_cuda_node_upsert(rio_placement *h, const char *address, uint32_t weight, const float *feat, uint32_t K, uint32_t *out_idx) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] {
+        REQUIRE(address, "address is NULL");
+        const uint32_t idx = intern_node(h, address);
+        NodeInfo &ni = h->nodes[idx];
+        ni.weight = weight;
+        ni.active = true;
+        if (feat) { REQUIRE(K > 0 && (h->K == 0 || h->K == K), "feature dimension mismatch"); h->K = K; ni.feat.assign(feat, feat + K); }
+        h->tab_dirty = true;
+        if (out_idx) *out_idx = idx;
+    });
+}
+
+rio_status rio_cuda_node_set_active(rio_placement *h, uint32_t idx, int32_t active) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] {
+        REQUIRE(idx < h->nodes.size(), "node index out of range");
+        h->nodes[idx].active = active != 0;
+        h->tab_dirty = true;
+    });
+}
+
+rio_status rio_cuda_node_index(rio_placement *h, const char *address, uint32_t *out_idx) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] {
+        REQUIRE(address && out_idx, "null argument");
+        auto it = h->node_index.find(address);
+        *out_idx = it == h->node_index.end() ? RIO_NONE : it->second;
+    });
+}
+
+rio_status rio_cuda_node_address(rio_placement *h, uint32_t idx, char *buf, size_t cap, size_t *out_len) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] {
+        REQUIRE(idx < h->nodes.size(), "node index out of range");
+        const std::string &a = h->nodes[idx].addr;
+        if (out_len) *out_len = a.size();
+        if (buf && cap) memcpy(buf, a.data(), std::min(cap, a.size()));
+    });
+}
+
+rio_status rio_cuda_node_count(rio_placement *h, uint32_t *out_total, uint32_t *out_live) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] {
+        if (out_total) *out_total = (uint32_t)h->nodes.size();
+        if (out_live) { uint32_t c = 0; for (auto &ni : h->nodes) c += ni.live(); *out_live = c; }
+    });
+}
+
+// ---- directory -----------------------------------------------------------------------------------------------------
+rio_status rio_cuda_lookup_batch(rio_placement *h, const uint64_t *keys, size_t n, uint32_t *out_idx) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] {
+        if (!n) return;
+        REQUIRE(keys && out_idx, "null buffer");
+        h->s_keys.ensure(n * 8, h->stream);
+        h->s_idx.ensure(n * 4, h->stream);
+        CUDA_TRY(cudaMemcpyAsync(h->s_keys.p, keys, n * 8, cudaMemcpyHostToDevice, h->stream));
+        launch_dir_lookup(h->L(), h->dir, h->s_keys.as<uint64_t>(), n, h->s_idx.as<uint32_t>());
+        CUDA_TRY(cudaMemcpyAsync(out_idx, h->s_idx.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    });
+}
+
+rio_status rio_cuda_upsert_batch(rio_placement *h, const uint64_t *keys, const uint32_t *idx, size_t n) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] {
+        if (!n) return;
+        REQUIRE(keys && idx, "null buffer");
+        dir_reserve(h, n);
+        h->s_keys.ensure(n * 8, h->stream);
+        h->s_idx.ensure(n * 4, h->stream);
+        CUDA_TRY(cudaMemcpyAsync(h->s_keys.p, keys, n * 8, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(h->s_idx.p, idx, n * 4, cudaMemcpyHostToDevice, h->stream));
+        dir_upsert_dev(h, h->s_keys.as<uint64_t>(), h->s_idx.as<uint32_t>(), 0, n);
+        reconcile_dir_keys(h);
+        check_device_error(h);
+    });
+}
+
+rio_status rio_cuda_remove_batch(rio_placement *h, const uint64_t *keys, size_t n) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] {
+        if (!n) return;
+        REQUIRE(keys, "null buffer");
+        dir_reserve(h, n);
+        h->s_keys.ensure(n * 8, h->stream);
+        CUDA_TRY(cudaMemcpyAsync(h->s_keys.p, keys, n * 8, cudaMemcpyHostToDevice, h->stream));
+        dir_upsert_dev(h, h->s_keys.as<uint64_t>(), nullptr, kNone, n);
+        reconcile_dir_keys(h);
+        check_device_error(h);
+    });
+}
+
+rio_status rio_cuda_clean_node(rio_placement *h, uint32_t idx, uint64_t *out_removed) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] {
+        if (idx == RIO_NONE || idx >= h->nodes.size()) { if (out_removed) *out_removed = 0; return; }   // unknown address: nothing recorded on it
+        zero_scalar(h, S_MOVED);
+        launch_dir_clean_node(h->L(), h->dir, idx, h->d_scalars + S_MOVED);
+        const uint64_t r = read_scalar(h, S_MOVED);
+        if (out_removed) *out_removed = r;
+    });
+}
+
+rio_status rio_cuda_directory_len(rio_placement *h, uint64_t *out_placed, uint64_t *out_slots) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] {
+        zero_scalar(h, S_PLACED);
+        launch_dir_count(h->L(), h->dir, h->d_scalars + S_PLACED, nullptr, 0);
+        const uint64_t p = read_scalar(h, S_PLACED);
+        if (out_placed) *out_placed = p;
+        if (out_slots) *out_slots = h->dir_cap;
+    });
+}
+
+rio_status rio_cuda_directory_reserve(rio_placement *h, uint64_t n_more) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] { dir_reserve(h, n_more); CUDA_TRY(cudaStreamSynchronize(h->stream)); });
+}
+
+rio_status rio_cuda_load_counters(rio_placement *h, uint32_t *out, uint32_t cap) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] {
+        const uint32_t n_total = (uint32_t)h->nodes.size();
+        REQUIRE(out && cap >= n_total, "counter buffer too small");
+        if (!n_total) return;
+        h->s_misc.ensure((size_t)n_total * 4, h->stream);
+        CUDA_TRY(cudaMemsetAsync(h->s_misc.p, 0, (size_t)n_total * 4, h->stream));
+        zero_scalar(h, S_PLACED);
+        launch_dir_count(h->L(), h->dir, h->d_scalars + S_PLACED, h->s_misc.as<uint32_t>(), n_total);
+        CUDA_TRY(cudaMemcpyAsync(out, h->s_misc.p, (size_t)n_total * 4, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    });
+}
+
+// ---- solver --------------------------------------------------------------------------------------------------------
+rio_status rio_cuda_assign_batch(rio_placement *h, const uint64_t *keys, const float *obj_feats, size_t n, uint32_t *out_idx) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] {
+        if (!n) return;
+        REQUIRE((keys || obj_feats) && out_idx, "null buffer");
+        if (!obj_feats) REQUIRE(keys, "keys is NULL");
+        static const uint64_t dummy = 0;
+        assign_host_pipelined(h, keys ? keys : &dummy, obj_feats, n, out_idx);
+    });
+}
+
+rio_status rio_cuda_assign_batch_dev(rio_placement *h, const uint64_t *d_keys, const float *d_obj_feats, size_t n, uint32_t *d_out_idx) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] {
+        if (!n) return;
+        REQUIRE(d_out_idx && (d_keys || d_obj_feats), "null buffer");
+        ensure_tab(h);
+        if (d_obj_feats) {
+            REQUIRE(h->K > 0, "assign with object features needs node features");
+            launch_assign_affinity(h->L(), d_obj_feats, n, h->d_fnode.as<float>(), h->d_live.as<uint32_t>(), h->tabs.tab.n_total, h->K, d_out_idx, nullptr, nullptr);
+        } else {
+            launch_assign_hrw(h->L(), d_keys, n, h->tabs.tab, d_out_idx, nullptr, nullptr, 0);
+        }
+    });
+}
+
+rio_status rio_cuda_lookup_batch_dev(rio_placement *h, const uint64_t *d_keys, size_t n, uint32_t *d_out_idx) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] { if (n) { REQUIRE(d_keys && d_out_idx, "null buffer"); launch_dir_lookup(h->L(), h->dir, d_keys, n, d_out_idx); } });
+}
+
+rio_status rio_cuda_upsert_batch_dev(rio_placement *h, const uint64_t *d_keys, const uint32_t *d_idx, size_t n) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] {
+        if (!n) return;
+        REQUIRE(d_keys && d_idx, "null buffer");
+        REQUIRE((h->dir_keys + h->dir_keys_pending + n) * 10 <= h->dir_cap * 9, "directory too small for an asynchronous upsert: call rio_cuda_directory_reserve first");
+        dir_upsert_dev(h, d_keys, d_idx, 0, n);
+        h->dir_keys_pending += n;
+    });
+}
+
+rio_status rio_cuda_place_batch(rio_placement *h, const uint64_t *keys, size_t n, uint32_t policy, uint32_t self_idx, uint32_t *out_idx) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] {
+        if (!n) return;
+        REQUIRE(keys && out_idx, "null buffer");
+        REQUIRE(policy == RIO_PLACE_SELF || policy == RIO_PLACE_HRW, "unknown policy");
+        REQUIRE(n < 0xFFFFFFFFull, "batch too large");
+        if (policy == RIO_PLACE_SELF) REQUIRE(self_idx < h->nodes.size(), "self_idx is not a known node");
+        ensure_tab(h);
+        const uint32_t n_total = h->tabs.tab.n_total;
+        cudaStream_t st = h->stream;
+        h->s_keys.ensure(n * 8, st);
+        h->s_idx.ensure(n * 4, st);
+        h->s_sel.ensure(n * 4, st);
+        h->s_misc.ensure(std::max<size_t>(n_total, 1), st);
+        CUDA_TRY(cudaMemcpyAsync(h->s_keys.p, keys, n * 8, cudaMemcpyHostToDevice, st));
+        launch_dir_lookup(h->L(), h->dir, h->s_keys.as<uint64_t>(), n, h->s_idx.as<uint32_t>());                          // service.rs:199-201
+        zero_scalar(h, S_NSEL);
+        CUDA_TRY(cudaMemsetAsync(h->s_misc.p, 0, std::max<size_t>(n_total, 1), st));
+        launch_classify(h->L(), h->s_idx.as<uint32_t>(), n, h->d_node_state.as<uint8_t>(), n_total, h->s_sel.as<uint32_t>(), h->d_scalars + S_NSEL,
+                        h->s_misc.as<uint8_t>());
+        const uint64_t nsel = read_scalar(h, S_NSEL);
+        if (nsel) {
+            // clean_server for every inactive node that was met (service.rs:233-237): one pass over the table for all of them
+            zero_scalar(h, S_MOVED);
+            launch_dir_clean_flagged(h->L(), h->dir, h->s_misc.as<uint8_t>(), n_total, h->d_scalars + S_MOVED);
+            if (policy == RIO_PLACE_SELF) launch_scatter_const(h->L(), h->s_idx.as<uint32_t>(), h->s_sel.as<uint32_t>(), nsel, self_idx);   // :244-252
+            else launch_assign_hrw(h->L(), h->s_keys.as<uint64_t>(), n, h->tabs.tab, h->s_idx.as<uint32_t>(), nullptr, h->s_sel.as<uint32_t>(), nsel);
+            h->s_keys2.ensure(nsel * 8, st);
+            h->s_idx2.ensure(nsel * 4, st);
+            launch_gather_keys(h->L(), h->s_keys.as<uint64_t>(), h->s_sel.as<uint32_t>(), nsel, h->s_keys2.as<uint64_t>(), h->s_idx.as<uint32_t>(),
+                               h->s_idx2.as<uint32_t>());
+            dir_reserve(h, nsel);
+            dir_upsert_dev(h, h->s_keys2.as<uint64_t>(), h->s_idx2.as<uint32_t>(), 0, nsel);
+        }
+        CUDA_TRY(cudaMemcpyAsync(out_idx, h->s_idx.p, n * 4, cudaMemcpyDeviceToHost, st));
+        if (nsel) { reconcile_dir_keys(h); check_device_error(h); } else CUDA_TRY(cudaStreamSynchronize(st));
+    });
+}
+
+rio_status rio_cuda_rebalance(rio_placement *h, uint32_t event, uint32_t idx, uint64_t *out_moved) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] {
+        REQUIRE(event == RIO_EV_JOIN || event == RIO_EV_LEAVE, "unknown event");
+        REQUIRE(idx < h->nodes.size(), "node index out of range");
+        ensure_tab(h);
+        zero_scalar(h, S_MOVED);
+        if (event == RIO_EV_JOIN) {
+            REQUIRE(h->nodes[idx].live(), "JOIN of a node that is not live");
+            launch_dir_rebalance_join(h->L(), h->dir, h->tabs.tab, idx, h->d_scalars + S_MOVED);
+        } else {
+            REQUIRE(!h->nodes[idx].live(), "LEAVE of a node that is still live (deactivate it first)");
+            launch_dir_rebalance_leave(h->L(), h->dir, h->tabs.tab, idx, h->d_scalars + S_MOVED);
+        }
+        const uint64_t m = read_scalar(h, S_MOVED);
+        if (out_moved) *out_moved = m;
+    });
+}
+
+// ---- resident object sets --------------------------------------------------------------------------------------------
+rio_status rio_cuda_set_create(rio_placement *h, uint64_t capacity, rio_objset **out) {
+    if (!h || !out) { g_last_error = "null argument"; return RIO_ERR_UNKNOWN; }
+    *out = nullptr;
+    rio_objset *s = new rio_objset();
+    rio_status st = guarded(h, [&] {
+        REQUIRE(capacity > 0 && capacity < 0xFFFFFFFFull, "set capacity must be in [1, 2^32-2]");
+        s->h = h;
+        s->capacity = capacity;
+        s->keys.ensure(capacity * 8, h->stream);
+        s->idx.ensure(capacity * 4, h->stream);
+        s->sel.ensure(capacity * 4, h->stream);
+        launch_fill_u32(h->L(), s->idx.as<uint32_t>(), capacity, kNone);
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    });
+    if (st != RIO_OK) { delete s; return st; }
+    *out = s;
+    return RIO_OK;
+}
+
+void rio_cuda_set_destroy(rio_objset *s) {
+    if (!s) return;
+    rio_placement *h = s->h;
+    {
+        std::lock_guard<std::mutex> g(h->mu);
+        cudaSetDevice(h->device);
+        s->keys.release(h->stream); s->idx.release(h->stream); s->feats.release(h->stream); s->counters.release(h->stream); s->sel.release(h->stream);
+        cudaStreamSynchronize(h->stream);
+    }
+    delete s;
+}
+
+rio_status rio_cuda_set_load_keys(rio_objset *s, const uint64_t *keys, uint64_t n) {
+    if (!s) { g_last_error = "null set"; return RIO_ERR_UNKNOWN; }
+    rio_placement *h = s->h;
+    return guarded(h, [&] {
+        REQUIRE(n <= s->capacity && (keys || !n), "too many keys for this set");
+        CUDA_TRY(cudaMemcpyAsync(s->keys.p, keys, n * 8, cudaMemcpyHostToDevice, h->stream));
+        s->n = n; s->assigned = false;
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    });
+}
+
+rio_status rio_cuda_set_synth_keys(rio_objset *s, uint64_t first, uint64_t n, uint64_t seed) {
+    if (!s) { g_last_error = "null set"; return RIO_ERR_UNKNOWN; }
+    rio_placement *h = s->h;
+    return guarded(h, [&] {
+        REQUIRE(n <= s->capacity, "too many keys for this set");
+        launch_synth_keys(h->L(), s->keys.as<uint64_t>(), first, n, seed);
+        s->n = n; s->assigned = false;
+    });
+}
+
+rio_status rio_cuda_set_load_feats(rio_objset *s, const float *feats, uint32_t K) {
+    if (!s) { g_last_error = "null set"; return RIO_ERR_UNKNOWN; }
+    rio_placement *h = s->h;
+    return guarded(h, [&] {
+        REQUIRE(feats && K > 0, "null features");
+        s->feats.ensure(s->n * (size_t)K * 4, h->stream);
+        CUDA_TRY(cudaMemcpyAsync(s->feats.p, feats, s->n * (size_t)K * 4, cudaMemcpyHostToDevice, h->stream));
+        s->K = K;
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    });
+}
+
+rio_status rio_cuda_set_assign(rio_objset *s, uint32_t use_affinity) {
+    if (!s) { g_last_error = "null set"; return RIO_ERR_UNKNOWN; }
+    rio_placement *h = s->h;
+    return guarded(h, [&] {
+        ensure_tab(h);
+        set_ensure_counters(s);
+        CUDA_TRY(cudaMemsetAsync(s->counters.p, 0, (size_t)std::max(s->counters_n, 1u) * 4, h->stream));
+        if (use_affinity) {
+            REQUIRE(s->K > 0 && s->K == h->K, "set features / node features missing or of different K");
+            launch_assign_affinity(h->L(), s->feats.as<float>(), s->n, h->d_fnode.as<float>(), h->d_live.as<uint32_t>(), h->tabs.tab.n_total, h->K,
+                                   s->idx.as<uint32_t>(), nullptr, s->counters.as<uint32_t>());
+        } else {
+            launch_assign_hrw(h->L(), s->keys.as<uint64_t>(), s->n, h->tabs.tab, s->idx.as<uint32_t>(), s->counters.as<uint32_t>(), nullptr, 0);
+        }
+        s->assigned = true;
+    });
+}
+
+rio_status rio_cuda_set_assign_bounded(rio_objset *s, uint64_t n_total_objs, uint32_t cap_num, uint32_t cap_den, uint32_t max_rounds, uint32_t *out_passes) {
+    if (!s) { g_last_error = "null set"; return RIO_ERR_UNKNOWN; }
+    rio_placement *h = s->h;
+    return guarded(h, [&] {
+        REQUIRE(cap_den > 0 && max_rounds > 0, "bad capacity factor / rounds");
+        ensure_tab(h);
+        set_ensure_counters(s);
+        const uint32_t M = s->counters_n;
+        if (!n_total_objs) n_total_objs = s->n * (uint64_t)h->world;
+        uint64_t W = 0;
+        for (auto &ni : h->nodes) if (ni.live()) W += ni.weight;
+        std::vector<uint32_t> cap(M, 0), thr(M, 0), cnt(M, 0);
+        std::vector<uint8_t> over(M, 0), closed(M, 0);
+        for (uint32_t j = 0; j < M; j++) if (h->nodes[j].live()) cap[j] = capacity_of(n_total_objs, h->nodes[j].weight, W, cap_num, cap_den);
+        cudaStream_t st = h->stream;
+        h->s_misc.ensure((size_t)std::max(M, 1u) * 9, st);   // [global counters u32 | thr u32 | over u8]
+        uint32_t *d_glob = h->s_misc.as<uint32_t>();
+        uint32_t *d_thr = d_glob + M;
+        uint8_t *d_over = reinterpret_cast<uint8_t *>(d_thr + M);
+        CUDA_TRY(cudaMemsetAsync(s->counters.p, 0, (size_t)std::max(M, 1u) * 4, st));
+        launch_assign_hrw(h->L(), s->keys.as<uint64_t>(), s->n, h->tabs.tab, s->idx.as<uint32_t>(), s->counters.as<uint32_t>(), nullptr, 0);
+        uint32_t passes = 1;
+        for (uint32_t r = 1; r < max_rounds; r++) {
+            exchange_counters(h, s->counters.as<uint32_t>(), d_glob, M);                  // the one collective of this pass
+            if (M) CUDA_TRY(cudaMemcpyAsync(cnt.data(), d_glob, (size_t)M * 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            bool any = false; uint32_t open = 0;
+            for (uint32_t j = 0; j < M; j++) {
+                over[j] = h->nodes[j].live() && cnt[j] > cap[j];
+                thr[j] = 0;
+                if (over[j]) { any = true; closed[j] = 1; thr[j] = (uint32_t)((((uint64_t)(cnt[j] - cap[j])) << 32) / cnt[j]); }
+            }
+            for (uint32_t j = 0; j < M; j++) open += h->nodes[j].live() && !closed[j];
+            if (!any || !open) break;
+            CUDA_TRY(cudaMemcpyAsync(d_thr, thr.data(), (size_t)M * 4, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(d_over, over.data(), M, cudaMemcpyHostToDevice, st));
+            zero_scalar(h, S_NSEL);
+            launch_select_spill(h->L(), s->keys.as<uint64_t>(), s->idx.as<uint32_t>(), s->n, d_thr, d_over, r, s->sel.as<uint32_t>(), h->d_scalars + S_NSEL,
+                                s->counters.as<uint32_t>());
+            const uint64_t nsel = read_scalar(h, S_NSEL);
+            build_tab(h, h->tabs_masked, &closed);
+            if (nsel) launch_assign_hrw(h->L(), s->keys.as<uint64_t>(), s->n, h->tabs_masked.tab, s->idx.as<uint32_t>(), s->counters.as<uint32_t>(), s->sel.as<uint32_t>(), nsel);
+            passes++;
+        }
+        s->assigned = true;
+        if (out_passes) *out_passes = passes;
+        CUDA_TRY(cudaStreamSynchronize(st));
+    });
+}
+
+rio_status rio_cuda_set_rebalance(rio_objset *s, uint32_t event, uint32_t idx, uint64_t *out_moved) {
+    if (!s) { g_last_error = "null set"; return RIO_ERR_UNKNOWN; }
+    rio_placement *h = s->h;
+    return guarded(h, [&] {
+        REQUIRE(event == RIO_EV_JOIN || event == RIO_EV_LEAVE, "unknown event");
+        REQUIRE(idx < h->nodes.size(), "node index out of range");
+        REQUIRE(s->assigned, "set has no assignment yet");
+        ensure_tab(h);
+        set_ensure_counters(s);
+        zero_scalar(h, S_MOVED);
+        uint64_t moved = 0;
+        if (event == RIO_EV_JOIN) {
+            REQUIRE(h->nodes[idx].live(), "JOIN of a node that is not live");
+            launch_rebalance_join(h->L(), s->keys.as<uint64_t>(), s->idx.as<uint32_t>(), s->n, h->tabs.tab, idx, s->counters.as<uint32_t>(), h->d_scalars + S_MOVED);
+            moved = read_scalar(h, S_MOVED);
+        } else {
+            REQUIRE(!h->nodes[idx].live(), "LEAVE of a node that is still live (deactivate it first)");
+            zero_scalar(h, S_NSEL);
+            launch_select_on_node(h->L(), s->idx.as<uint32_t>(), s->n, idx, s->sel.as<uint32_t>(), h->d_scalars + S_NSEL);
+            moved = read_scalar(h, S_NSEL);
+            CUDA_TRY(cudaMemsetAsync(s->counters.as<uint32_t>() + idx, 0, 4, h->stream));
+            if (moved) launch_assign_hrw(h->L(), s->keys.as<uint64_t>(), s->n, h->tabs.tab, s->idx.as<uint32_t>(), s->counters.as<uint32_t>(), s->sel.as<uint32_t>(), moved);
+        }
+        if (out_moved) *out_moved = moved;
+    });
+}
+
+rio_status rio_cuda_set_counters(rio_objset *s, uint32_t *out, uint32_t cap) {
+    if (!s) { g_last_error = "null set"; return RIO_ERR_UNKNOWN; }
+    rio_placement *h = s->h;
+    return guarded(h, [&] {
+        set_ensure_counters(s);
+        const uint32_t M = s->counters_n;
+        REQUIRE(out && cap >= M, "counter buffer too small");
+        if (!M) return;
+        h->s_misc.ensure((size_t)M * 4, h->stream);
+        exchange_counters(h, s->counters.as<uint32_t>(), h->s_misc.as<uint32_t>(), M);
+        CUDA_TRY(cudaMemcpyAsync(out, h->s_misc.p, (size_t)M * 4, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    });
+}
+
+rio_status rio_cuda_set_read(rio_objset *s, uint64_t first, uint64_t n, uint64_t *out_keys, uint32_t *out_idx) {
+    if (!s) { g_last_error = "null set"; return RIO_ERR_UNKNOWN; }
+    rio_placement *h = s->h;
+    return guarded(h, [&] {
+        REQUIRE(first + n <= s->n, "range outside the set");
+        if (out_keys && n) CUDA_TRY(cudaMemcpyAsync(out_keys, s->keys.as<uint64_t>() + first, n * 8, cudaMemcpyDeviceToHost, h->stream));
+        if (out_idx && n) CUDA_TRY(cudaMemcpyAsync(out_idx, s->idx.as<uint32_t>() + first, n * 4, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    });
+}
+
+rio_status rio_cuda_set_size(rio_objset *s, uint64_t *out_n) {
+    if (!s || !out_n) { g_last_error = "null argument"; return RIO_ERR_UNKNOWN; }
+    *out_n = s->n;
+    return RIO_OK;
+}
+
+rio_status rio_cuda_set_commit(rio_objset *s) {
+    if (!s) { g_last_error = "null set"; return RIO_ERR_UNKNOWN; }
+    rio_placement *h = s->h;
+    return guarded(h, [&] {
+        REQUIRE(s->assigned, "set has no assignment yet");
+        dir_reserve(h, s->n);
+        dir_upsert_dev(h, s->keys.as<uint64_t>(), s->idx.as<uint32_t>(), 0, s->n);
+        reconcile_dir_keys(h);
+        check_device_error(h);
+    });
+}
+
+// ---- multi-GPU ---------------------------------------------------------------------------------------------------------
+rio_status rio_cuda_comm_unique_id(uint8_t out_id[RIO_COMM_ID_BYTES]) {
+    return guarded(nullptr, [&] {
+        std::lock_guard<std::mutex> g(g_nccl_mu);
+        if (!g_nccl.load()) throw RioError{RIO_ERR_UPSTREAM, "cannot load libnccl: " + g_nccl.load_error};
+        NcclId id;
+        NCCL_TRY(g_nccl.GetUniqueId(&id));
+        memcpy(out_id, id.internal, RIO_COMM_ID_BYTES);
+    });
+}
+
+rio_status rio_cuda_comm_init(rio_placement *h, int32_t rank, int32_t world, const uint8_t id[RIO_COMM_ID_BYTES]) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] {
+        REQUIRE(world >= 1 && rank >= 0 && rank < world && id, "bad rank/world");
+        {
+            std::lock_guard<std::mutex> g(g_nccl_mu);
+            if (!g_nccl.load()) throw RioError{RIO_ERR_UPSTREAM, "cannot load libnccl: " + g_nccl.load_error};
+        }
+        if (h->comm) { g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
+        NcclId nid;
+        memcpy(nid.internal, id, RIO_COMM_ID_BYTES);
+        NCCL_TRY(g_nccl.CommInitRank(&h->comm, world, nid, rank));
+        h->rank = rank; h->world = world;
+    });
+}
+
+rio_status rio_cuda_comm_info(rio_placement *h, int32_t *rank, int32_t *world) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    if (rank) *rank = h->rank;
+    if (world) *world = h->world;
+    return RIO_OK;
+}
+
+rio_status rio_cuda_comm_sum_counters(rio_placement *h, uint32_t *inout, uint32_t M) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] {
+        if (!M) return;
+        REQUIRE(inout, "null buffer");
+        h->s_misc.ensure((size_t)M * 8, h->stream);
+        uint32_t *d_in = h->s_misc.as<uint32_t>(), *d_out = d_in + M;
+        CUDA_TRY(cudaMemcpyAsync(d_in, inout, (size_t)M * 4, cudaMemcpyHostToDevice, h->stream));
+        exchange_counters(h, d_in, d_out, M);
+        CUDA_TRY(cudaMemcpyAsync(inout, d_out, (size_t)M * 4, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    });
+}
+
+// ---- device memory / timing helpers --------------------------------------------------------------------------------
+rio_status rio_cuda_dev_alloc(rio_placement *h, size_t bytes, void **out_dev) {
+    if (!h || !out_dev) { g_last_error = "null argument"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] { CUDA_TRY(cudaMalloc(out_dev, bytes ? bytes : 1)); });
+}
+rio_status rio_cuda_dev_free(rio_placement *h, void *dev) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] { CUDA_TRY(cudaStreamSynchronize(h->stream)); if (dev) CUDA_TRY(cudaFree(dev)); });
+}
+rio_status rio_cuda_host_alloc(rio_placement *h, size_t bytes, void **out_pinned) {
+    if (!h || !out_pinned) { g_last_error = "null argument"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] { CUDA_TRY(cudaMallocHost(out_pinned, bytes ? bytes : 1)); });
+}
+rio_status rio_cuda_host_free(rio_placement *h, void *pinned) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] { if (pinned) CUDA_TRY(cudaFreeHost(pinned)); });
+}
+rio_status rio_cuda_memcpy_h2d(rio_placement *h, void *dev, const void *host, size_t bytes) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] { if (bytes) CUDA_TRY(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, h->stream)); });
+}
+rio_status rio_cuda_memcpy_d2h(rio_placement *h, void *host, const void *dev, size_t bytes) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] { if (bytes) CUDA_TRY(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, h->stream)); });
+}
+rio_status rio_cuda_flush_l2(rio_placement *h) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] {
+        const size_t words = (size_t)64 << 20;   // 256 MiB > 126 MB of L2
+        h->s_flush.ensure(words * 4, h->stream);
+        static uint32_t v = 0;
+        launch_l2_flush(h->L(), h->s_flush.as<uint32_t>(), words, ++v);
+    });
+}
+rio_status rio_cuda_bench_mix_rate(rio_placement *h, uint32_t iters, double *out_pairs_per_s) {
+    if (!h || !out_pairs_per_s) { g_last_error = "null argument"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] {
+        h->s_misc.ensure(4096, h->stream);
+        {   // opaque per-object constants for the probe
+            std::vector<uint32_t> seed(1024);
+            for (uint32_t i = 0; i < 1024; i++) seed[i] = (uint32_t)mix64(i + 1);
+            CUDA_TRY(cudaMemcpyAsync(h->s_misc.p, seed.data(), 4096, cudaMemcpyHostToDevice, h->stream));
+            CUDA_TRY(cudaStreamSynchronize(h->stream));
+        }
+        launch_mix_rate(h->L(), 16, h->s_misc.as<uint32_t>());   // warm-up
+        CUDA_TRY(cudaEventRecord(h->events[RIO_MAX_EVENTS - 2], h->stream));
+        const uint64_t pairs = launch_mix_rate(h->L(), iters ? iters : 1, h->s_misc.as<uint32_t>());
+        CUDA_TRY(cudaEventRecord(h->events[RIO_MAX_EVENTS - 1], h->stream));
+        CUDA_TRY(cudaEventSynchronize(h->events[RIO_MAX_EVENTS - 1]));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, h->events[RIO_MAX_EVENTS - 2], h->events[RIO_MAX_EVENTS - 1]));
+        *out_pairs_per_s = (double)pairs / ((double)ms * 1e-3);
+    });
+}
+rio_status rio_cuda_event_record(rio_placement *h, uint32_t slot) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] { REQUIRE(slot < RIO_MAX_EVENTS, "event slot out of range"); CUDA_TRY(cudaEventRecord(h->events[slot], h->stream)); });
+}
+rio_status rio_cuda_event_elapsed_ms(rio_placement *h, uint32_t a, uint32_t b, float *out_ms) {
+    if (!h || !out_ms) { g_last_error = "null argument"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] {
+        REQUIRE(a < RIO_MAX_EVENTS && b < RIO_MAX_EVENTS, "event slot out of range");
+        CUDA_TRY(cudaEventSynchronize(h->events[b]));
+        CUDA_TRY(cudaEventElapsedTime(out_ms, h->events[a], h->events[b]));
+    });
+}
+rio_status rio_cuda_launch_count(rio_placement *h, uint64_t *out) {
+    if (!h || !out) { g_last_error = "null argument"; return RIO_ERR_UNKNOWN; }
+    std::lock_guard<std::mutex> g(h->mu);
+    *out = h->launches;
+    return RIO_OK;
+}
+
+// ---- string-level provider calls (what impl ObjectPlacement for GpuObjectPlacement forwards) ---------------------------------
+rio_status rio_cuda_update_str(rio_placement *h, const char *type, size_t type_len, const char *id, size_t id_len, const char *address, size_t address_len) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] {
+        REQUIRE(type && id, "null id");
+        const uint64_t key = rio_cuda_object_key(type, type_len, id, id_len);
+        uint32_t idx = kNone;
+        if (address) idx = intern_node(h, std::string(address, address_len));     // any address may be recorded, live or not (local.rs:34-36)
+        dir_reserve(h, 1);
+        h->s_keys.ensure(8, h->stream);
+        CUDA_TRY(cudaMemcpyAsync(h->s_keys.p, &key, 8, cudaMemcpyHostToDevice, h->stream));
+        dir_upsert_dev(h, h->s_keys.as<uint64_t>(), nullptr, idx, 1);
+        reconcile_dir_keys(h);
+        check_device_error(h);
+    });
+}
+
+rio_status rio_cuda_lookup_str(rio_placement *h, const char *type, size_t type_len, const char *id, size_t id_len, char *buf, size_t cap, size_t *out_len) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] {
+        REQUIRE(type && id && out_len, "null argument");
+        const uint64_t key = rio_cuda_object_key(type, type_len, id, id_len);
+        h->s_keys.ensure(8, h->stream);
+        h->s_idx.ensure(4, h->stream);
+        CUDA_TRY(cudaMemcpyAsync(h->s_keys.p, &key, 8, cudaMemcpyHostToDevice, h->stream));
+        launch_dir_lookup(h->L(), h->dir, h->s_keys.as<uint64_t>(), 1, h->s_idx.as<uint32_t>());
+        uint32_t idx = kNone;
+        CUDA_TRY(cudaMemcpyAsync(&idx, h->s_idx.p, 4, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        if (idx == kNone || idx >= h->nodes.size()) { *out_len = (size_t)-1; return; }
+        const std::string &a = h->nodes[idx].addr;
+        *out_len = a.size();
+        if (buf && cap) memcpy(buf, a.data(), std::min(cap, a.size()));
+    });
+}
+
+rio_status rio_cuda_clean_server_str(rio_placement *h, const char *address, size_t address_len) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] {
+        REQUIRE(address, "null address");
+        auto it = h->node_index.find(std::string(address, address_len));
+        if (it == h->node_index.end()) return;   // never recorded: retain() would remove nothing (local.rs:56)
+        zero_scalar(h, S_MOVED);
+        launch_dir_clean_node(h->L(), h->dir, it->second, h->d_scalars + S_MOVED);
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    });
+}
+
+rio_status rio_cuda_remove_str(rio_placement *h, const char *type, size_t type_len, const char *id, size_t id_len) {
+    return rio_cuda_update_str(h, type, type_len, id, id_len, nullptr, 0);
+}
+
+}  // extern "C"

@@ -1,0 +1,423 @@
+// k_directory.cu -- the placement directory in HBM (batched LocalObjectPlacement, local.rs:12-68) and the
+// streaming rebalance kernels.  Integer/byte work, HBM-bound: one 16-byte slot per probe (a 32-byte sector holds
+// two slots), 128-bit loads on the scans, warp-aggregated counters.
+#include "kernels.cuh"
+#include "spec.cuh"
+
+namespace rio {
+
+namespace {
+
+#define RIO_COUNT_LAUNCH(L) do { if ((L).launch_counter) ++*(L).launch_counter; } while (0)
+
+inline int grid_for(uint64_t work_items, int threads, int sm_count, int blocks_per_sm) {
+    uint64_t blocks = (work_items + threads - 1) / threads;
+    uint64_t cap = (uint64_t)sm_count * blocks_per_sm;
+    if (blocks < 1) blocks = 1;
+    return (int)(blocks < cap ? blocks : cap);
+}
+
+__device__ __forceinline__ unsigned long long norm_key(uint64_t k) {
+    // kEmptyKey is reserved for free slots: fold it onto its neighbour (documented)
+    return k == kEmptyKey ? kEmptyKey - 1 : k;
+}
+__device__ __forceinline__ uint64_t home_slot(unsigned long long key, const DirDev &d) {
+    return (key * kGolden64) >> d.shift;   // Fibonacci hashing: keys may be raw user u64s
+}
+
+__device__ __forceinline__ void warp_add(unsigned long long *ctr, bool pred) {
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, pred);
+    if (m && (threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) atomicAdd(ctr, (unsigned long long)__popc(m));
+}
+
+__global__ void k_dir_init(DirSlot *slots, uint64_t cap) {
+    uint4 *p = reinterpret_cast<uint4 *>(slots);
+    const uint4 e = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u);  // key = EMPTY, val = (0 << 32) | NONE
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) p[i] = e;
+}
+
+// lookup (local.rs:42-49)
+__global__ void __launch_bounds__(256)
+k_dir_lookup(DirDev dir, const uint64_t *__restrict__ keys, uint64_t n, uint32_t *__restrict__ out) {
+    const uint4 *slots = reinterpret_cast<const uint4 *>(dir.slots);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned long long key = norm_key(__ldg(keys + i));
+        uint64_t s = home_slot(key, dir);
+        uint32_t res = kNone;
+        for (uint64_t probes = 0; probes <= dir.mask; probes++) {
+            const uint4 v = slots[s];   // one 16-byte load: key + value together
+            const unsigned long long k = ((unsigned long long)v.y << 32) | v.x;
+            if (k == key) { res = v.z; break; }
+            if (k == kEmptyKey) break;
+            s = (s + 1) & dir.mask;
+        }
+        out[i] = res;
+    }
+}
+
+// update (local.rs:22-40), batched.  Claim-or-find the slot with a 64-bit CAS on the key, then order duplicate keys of
+// the same batch with a 64-bit atomicMax on (seq << 32 | node): seq = position + 1, so the last one in array order wins.
+// k_dir_upsert_finish then clears seq.
+__global__ void __launch_bounds__(256)
+k_dir_upsert(DirDev dir, const uint64_t *__restrict__ keys, const uint32_t *__restrict__ idx, uint32_t const_idx, uint64_t n,
+             uint64_t *__restrict__ slot_scratch, unsigned long long *new_keys, uint32_t *error) {
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = base + threadIdx.x;
+        bool fresh = false;
+        if (i < n) {
+            const unsigned long long key = norm_key(__ldg(keys + i));
+            const uint32_t node = idx ? __ldg(idx + i) : const_idx;
+            uint64_t s = home_slot(key, dir);
+            bool placed = false;
+            for (uint64_t probes = 0; probes <= dir.mask; probes++) {
+                unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(&dir.slots[s].key);
+                if (k == kEmptyKey) {
+                    k = atomicCAS(&dir.slots[s].key, kEmptyKey, key);
+                    if (k == kEmptyKey) { fresh = true; k = key; }
+                }
+                if (k == key) { placed = true; break; }
+                s = (s + 1) & dir.mask;
+            }
+            if (placed) {
+                atomicMax(&dir.slots[s].val, ((unsigned long long)(i + 1) << 32) | node);
+                slot_scratch[i] = s;
+            } else {
+                slot_scratch[i] = ~0ull;
+                atomicExch(error, 1u);   // table full: the host sizes the table so this cannot happen
+            }
+        }
+        warp_add(new_keys, fresh);   // whole warp reaches this point (base loop is block-uniform)
+    }
+}
+__global__ void __launch_bounds__(256)
+k_dir_upsert_finish(DirDev dir, const uint64_t *__restrict__ slot_scratch, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t s = slot_scratch[i];
+        if (s != ~0ull) reinterpret_cast<uint32_t *>(&dir.slots[s].val)[1] = 0;   // idempotent for duplicates
+    }
+}
+
+// clean_server (local.rs:51-58): streaming scan, the GPU analogue of retain(|_, v| *v != address)
+__global__ void __launch_bounds__(256)
+k_dir_clean_node(DirDev dir, uint32_t node, unsigned long long *removed) {
+    uint4 *slots = reinterpret_cast<uint4 *>(dir.slots);
+    const uint64_t cap = dir.mask + 1;
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < cap; base += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = base + threadIdx.x;
+        bool hit = false;
+        if (i < cap) {
+            const uint4 v = slots[i];
+            hit = v.z == node && (v.x & v.y) != 0xFFFFFFFFu;
+            if (hit) reinterpret_cast<uint32_t *>(&dir.slots[i].val)[0] = kNone;
+        }
+        warp_add(removed, hit);
+    }
+}
+// same, for a set of nodes flagged in a byte map (place_batch cleans every dead node it met in one pass)
+__global__ void __launch_bounds__(256)
+k_dir_clean_flagged(DirDev dir, const uint8_t *__restrict__ flag, uint32_t n_total, unsigned long long *removed) {
+    uint4 *slots = reinterpret_cast<uint4 *>(dir.slots);
+    const uint64_t cap = dir.mask + 1;
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < cap; base += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = base + threadIdx.x;
+        bool hit = false;
+        if (i < cap) {
+            const uint4 v = slots[i];
+            hit = v.z < n_total && (v.x & v.y) != 0xFFFFFFFFu && __ldg(flag + v.z);
+            if (hit) reinterpret_cast<uint32_t *>(&dir.slots[i].val)[0] = kNone;
+        }
+        warp_add(removed, hit);
+    }
+}
+
+// grow: re-insert every placed key of `from` into the (empty) table `to`; unplaced keys are dropped
+__global__ void __launch_bounds__(256)
+k_dir_rehash(DirDev from, DirDev to, unsigned long long *new_keys, uint32_t *error) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(from.slots);
+    const uint64_t cap = from.mask + 1;
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < cap; base += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = base + threadIdx.x;
+        bool moved = false;
+        if (i < cap) {
+            const uint4 v = src[i];
+            const unsigned long long key = ((unsigned long long)v.y << 32) | v.x;
+            if (key != kEmptyKey && v.z != kNone) {
+                uint64_t s = home_slot(key, to);
+                for (uint64_t probes = 0; probes <= to.mask; probes++) {
+                    const unsigned long long k = atomicCAS(&to.slots[s].key, kEmptyKey, key);
+                    if (k == kEmptyKey) { to.slots[s].val = v.z; moved = true; break; }   // keys of `from` are distinct
+                    s = (s + 1) & to.mask;
+                }
+                if (!moved) atomicExch(error, 1u);
+            }
+        }
+        warp_add(new_keys, moved);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_dir_count(DirDev dir, unsigned long long *placed, uint32_t *counters, uint32_t n_total) {
+    const uint4 *slots = reinterpret_cast<const uint4 *>(dir.slots);
+    const uint64_t cap = dir.mask + 1;
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < cap; base += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = base + threadIdx.x;
+        bool hit = false;
+        if (i < cap) {
+            const uint4 v = slots[i];
+            hit = (v.x & v.y) != 0xFFFFFFFFu && v.z != kNone;
+            if (hit && counters && v.z < n_total) atomicAdd(&counters[v.z], 1u);
+        }
+        warp_add(placed, hit);
+    }
+}
+
+// ---- rebalance ---------------------------------------------------------------------------------------
+// JOIN(new): an object moves iff the new node beats its incumbent under the spec order (score, ~u, j); both
+// candidates are one pair hash each (the incumbent's is recomputed from (key, idx) instead of being stored, so
+// the stream is 12 B/object for a dense set, 16 B/slot for the directory).  by_idx[] gives {s0, invw, s2}.
+__device__ __forceinline__ bool join_wins(uint64_t key, uint32_t cur, uint32_t new_idx, const uint4 nn, const uint4 *__restrict__ by_idx) {
+    const ObjHash o = obj_hash(key);
+    const uint32_t un = pair_hash(o, nn.x, ((uint64_t)nn.w << 32) | nn.z);
+    const uint64_t sn = (uint64_t)elog(un) * nn.y;
+    const uint4 c = __ldg(by_idx + cur);
+    if (c.y == 0) return true;   // incumbent is not live any more
+    const uint32_t uc = pair_hash(o, c.x, ((uint64_t)c.w << 32) | c.z);
+    const uint64_t sc = (uint64_t)elog(uc) * c.y;
+    return cand_better(sn, un, new_idx, sc, uc, cur);
+}
+
+__global__ void __launch_bounds__(256)
+k_rebalance_join(const uint64_t *__restrict__ keys, uint32_t *__restrict__ idx, uint64_t n, NodeTabDev tab, uint32_t new_idx,
+                 uint32_t *__restrict__ counters, unsigned long long *moved) {
+    const uint4 nn = __ldg(tab.by_idx + new_idx);
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = base + threadIdx.x;
+        bool mv = false;
+        if (i < n) {
+            const uint32_t cur = idx[i];
+            if (cur != new_idx && cur < tab.n_total && nn.y) {
+                mv = join_wins(__ldg(keys + i), cur, new_idx, nn, tab.by_idx);
+                if (mv) { idx[i] = new_idx; if (counters) { atomicSub(&counters[cur], 1u); atomicAdd(&counters[new_idx], 1u); } }
+            }
+        }
+        warp_add(moved, mv);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_dir_rebalance_join(DirDev dir, NodeTabDev tab, uint32_t new_idx, unsigned long long *moved) {
+    const uint4 *slots = reinterpret_cast<const uint4 *>(dir.slots);
+    const uint4 nn = __ldg(tab.by_idx + new_idx);
+    const uint64_t cap = dir.mask + 1;
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < cap; base += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = base + threadIdx.x;
+        bool mv = false;
+        if (i < cap) {
+            const uint4 v = slots[i];
+            const unsigned long long key = ((unsigned long long)v.y << 32) | v.x;
+            if (key != kEmptyKey && v.z != kNone && v.z != new_idx && v.z < tab.n_total && nn.y) {
+                mv = join_wins(key, v.z, new_idx, nn, tab.by_idx);
+                if (mv) reinterpret_cast<uint32_t *>(&dir.slots[i].val)[0] = new_idx;
+            }
+        }
+        warp_add(moved, mv);
+    }
+}
+
+// LEAVE(gone): pick the objects recorded on the node (4 B/object scan) into a compact list ...
+__global__ void __launch_bounds__(256)
+k_select_on_node(const uint32_t *__restrict__ idx, uint64_t n, uint32_t node, uint32_t *__restrict__ sel, unsigned long long *nsel) {
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = base + threadIdx.x;
+        const bool hit = i < n && __ldg(idx + i) == node;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
+        if (m) {
+            const unsigned lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+            unsigned long long b = 0;
+            if (lane == leader) b = atomicAdd(nsel, (unsigned long long)__popc(m));
+            b = __shfl_sync(0xFFFFFFFFu, b, leader);
+            if (hit) sel[b + __popc(m & ((1u << lane) - 1))] = (uint32_t)i;
+        }
+    }
+}
+// ... and, for the directory, re-place them in the same pass (warp per hit would be nicer; hits are ~cap/M so a
+// thread-serial walk of the class-sorted table from global/L2 is enough here).
+__device__ uint32_t hrw_scalar(uint64_t key, const NodeTabDev &tab) {
+    const ObjHash o = obj_hash(key);
+    const uint4 *grec = reinterpret_cast<const uint4 *>(tab.recs);
+    uint64_t best_sc = ~0ull; uint32_t best_u = 0, best_i = kNone;
+    for (uint32_t c = 0; c < tab.n_classes; c++) {
+        const ClassRec r0 = tab.classes[c], r1 = tab.classes[c + 1];
+        uint32_t cu = 0, ci = kNone;
+        for (uint32_t q = r0.start; q < r1.start; q++) {
+            const uint4 r = __ldg(grec + q);
+            const uint32_t u = pair_hash(o, r.x, ((uint64_t)r.w << 32) | r.z);
+            if (ci == kNone || u > cu) { cu = u; ci = r.y; }
+        }
+        const uint64_t sc = (uint64_t)elog(cu) * r0.invw;
+        if (ci != kNone && (best_i == kNone || cand_better(sc, cu, ci, best_sc, best_u, best_i))) { best_sc = sc; best_u = cu; best_i = ci; }
+    }
+    return best_i;
+}
+__global__ void __launch_bounds__(256)
+k_dir_rebalance_leave(DirDev dir, NodeTabDev tab, uint32_t gone, unsigned long long *moved) {
+    const uint4 *slots = reinterpret_cast<const uint4 *>(dir.slots);
+    const uint64_t cap = dir.mask + 1;
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < cap; base += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = base + threadIdx.x;
+        bool mv = false;
+        if (i < cap) {
+            const uint4 v = slots[i];
+            const unsigned long long key = ((unsigned long long)v.y << 32) | v.x;
+            if (key != kEmptyKey && v.z == gone) {
+                reinterpret_cast<uint32_t *>(&dir.slots[i].val)[0] = hrw_scalar(key, tab);
+                mv = true;
+            }
+        }
+        warp_add(moved, mv);
+    }
+}
+
+// bounded-load rounds: spill selection
+__global__ void __launch_bounds__(256)
+k_select_spill(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ idx, uint64_t n, const uint32_t *__restrict__ thr,
+               const uint8_t *__restrict__ over, uint32_t round, uint32_t *__restrict__ sel, unsigned long long *nsel, uint32_t *__restrict__ counters) {
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = base + threadIdx.x;
+        bool hit = false;
+        if (i < n) {
+            const uint32_t j = __ldg(idx + i);
+            if (j != kNone && __ldg(over + j)) {
+                hit = spill_hash(__ldg(keys + i), round) < __ldg(thr + j);
+                if (hit && counters) atomicSub(&counters[j], 1u);
+            }
+        }
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
+        if (m) {
+            const unsigned lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+            unsigned long long b = 0;
+            if (lane == leader) b = atomicAdd(nsel, (unsigned long long)__popc(m));
+            b = __shfl_sync(0xFFFFFFFFu, b, leader);
+            if (hit) sel[b + __popc(m & ((1u << lane) - 1))] = (uint32_t)i;
+        }
+    }
+}
+
+// place_batch: which looked-up placements must be (re)placed (service.rs:203-238)
+__global__ void __launch_bounds__(256)
+k_classify(const uint32_t *__restrict__ cur, uint64_t n, const uint8_t *__restrict__ node_state, uint32_t n_total, uint32_t *__restrict__ sel,
+           unsigned long long *nsel, uint8_t *__restrict__ dead_flag) {
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = base + threadIdx.x;
+        bool need = false;
+        if (i < n) {
+            const uint32_t c = __ldg(cur + i);
+            if (c == kNone || c >= n_total) need = true;                                  // service.rs:241-252
+            else {
+                const uint8_t st = __ldg(node_state + c);
+                if (!(st & kNodeLive)) { need = true; if (!(st & kNodeMalformed)) dead_flag[c] = 1; }   // :226-238 / :213-222
+            }
+        }
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, need);
+        if (m) {
+            const unsigned lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+            unsigned long long b = 0;
+            if (lane == leader) b = atomicAdd(nsel, (unsigned long long)__popc(m));
+            b = __shfl_sync(0xFFFFFFFFu, b, leader);
+            if (need) sel[b + __popc(m & ((1u << lane) - 1))] = (uint32_t)i;
+        }
+    }
+}
+
+__global__ void k_scatter_const(uint32_t *__restrict__ out, const uint32_t *__restrict__ sel, uint64_t n_sel, uint32_t v) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_sel; i += (uint64_t)gridDim.x * blockDim.x) out[sel[i]] = v;
+}
+__global__ void k_gather_keys(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ sel, uint64_t n_sel, uint64_t *__restrict__ out_keys,
+                              const uint32_t *__restrict__ idx, uint32_t *__restrict__ out_idx) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_sel; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t s = sel[i];
+        out_keys[i] = keys[s];
+        if (idx) out_idx[i] = idx[s];
+    }
+}
+
+}  // namespace
+
+void launch_dir_init(const Launch &L, DirSlot *slots, uint64_t cap) {
+    k_dir_init<<<grid_for(cap, 256, L.sm_count, 8), 256, 0, L.stream>>>(slots, cap);
+    RIO_COUNT_LAUNCH(L);
+}
+void launch_dir_lookup(const Launch &L, const DirDev &dir, const uint64_t *d_keys, uint64_t n, uint32_t *d_out) {
+    if (!n) return;
+    k_dir_lookup<<<grid_for(n, 256, L.sm_count, 8), 256, 0, L.stream>>>(dir, d_keys, n, d_out);
+    RIO_COUNT_LAUNCH(L);
+}
+void launch_dir_upsert(const Launch &L, const DirDev &dir, const uint64_t *d_keys, const uint32_t *d_idx, uint32_t const_idx, uint64_t n,
+                       uint64_t *d_slot_scratch, unsigned long long *d_new_keys, uint32_t *d_error) {
+    if (!n) return;
+    const int grid = grid_for(n, 256, L.sm_count, 8);
+    k_dir_upsert<<<grid, 256, 0, L.stream>>>(dir, d_keys, d_idx, const_idx, n, d_slot_scratch, d_new_keys, d_error);
+    RIO_COUNT_LAUNCH(L);
+    k_dir_upsert_finish<<<grid, 256, 0, L.stream>>>(dir, d_slot_scratch, n);
+    RIO_COUNT_LAUNCH(L);
+}
+void launch_dir_clean_node(const Launch &L, const DirDev &dir, uint32_t node, unsigned long long *d_removed) {
+    k_dir_clean_node<<<grid_for(dir.mask + 1, 256, L.sm_count, 8), 256, 0, L.stream>>>(dir, node, d_removed);
+    RIO_COUNT_LAUNCH(L);
+}
+void launch_dir_clean_flagged(const Launch &L, const DirDev &dir, const uint8_t *d_flag, uint32_t n_total, unsigned long long *d_removed) {
+    k_dir_clean_flagged<<<grid_for(dir.mask + 1, 256, L.sm_count, 8), 256, 0, L.stream>>>(dir, d_flag, n_total, d_removed);
+    RIO_COUNT_LAUNCH(L);
+}
+void launch_dir_rehash(const Launch &L, const DirDev &from, const DirDev &to, unsigned long long *d_new_keys, uint32_t *d_error) {
+    k_dir_rehash<<<grid_for(from.mask + 1, 256, L.sm_count, 8), 256, 0, L.stream>>>(from, to, d_new_keys, d_error);
+    RIO_COUNT_LAUNCH(L);
+}
+void launch_dir_count(const Launch &L, const DirDev &dir, unsigned long long *d_placed, uint32_t *d_counters, uint32_t n_total) {
+    k_dir_count<<<grid_for(dir.mask + 1, 256, L.sm_count, 8), 256, 0, L.stream>>>(dir, d_placed, d_counters, n_total);
+    RIO_COUNT_LAUNCH(L);
+}
+void launch_dir_rebalance_join(const Launch &L, const DirDev &dir, const NodeTabDev &tab, uint32_t new_idx, unsigned long long *d_moved) {
+    k_dir_rebalance_join<<<grid_for(dir.mask + 1, 256, L.sm_count, 8), 256, 0, L.stream>>>(dir, tab, new_idx, d_moved);
+    RIO_COUNT_LAUNCH(L);
+}
+void launch_dir_rebalance_leave(const Launch &L, const DirDev &dir, const NodeTabDev &tab, uint32_t gone_idx, unsigned long long *d_moved) {
+    k_dir_rebalance_leave<<<grid_for(dir.mask + 1, 256, L.sm_count, 8), 256, 0, L.stream>>>(dir, tab, gone_idx, d_moved);
+    RIO_COUNT_LAUNCH(L);
+}
+void launch_rebalance_join(const Launch &L, const uint64_t *d_keys, uint32_t *d_idx, uint64_t n, const NodeTabDev &tab, uint32_t new_idx,
+                           uint32_t *d_counters, unsigned long long *d_moved) {
+    if (!n) return;
+    k_rebalance_join<<<grid_for(n, 256, L.sm_count, 8), 256, 0, L.stream>>>(d_keys, d_idx, n, tab, new_idx, d_counters, d_moved);
+    RIO_COUNT_LAUNCH(L);
+}
+void launch_select_on_node(const Launch &L, const uint32_t *d_idx, uint64_t n, uint32_t node, uint32_t *d_sel, unsigned long long *d_nsel) {
+    if (!n) return;
+    k_select_on_node<<<grid_for(n, 256, L.sm_count, 8), 256, 0, L.stream>>>(d_idx, n, node, d_sel, d_nsel);
+    RIO_COUNT_LAUNCH(L);
+}
+void launch_select_spill(const Launch &L, const uint64_t *d_keys, const uint32_t *d_idx, uint64_t n, const uint32_t *d_thr, const uint8_t *d_over,
+                         uint32_t round, uint32_t *d_sel, unsigned long long *d_nsel, uint32_t *d_counters) {
+    if (!n) return;
+    k_select_spill<<<grid_for(n, 256, L.sm_count, 8), 256, 0, L.stream>>>(d_keys, d_idx, n, d_thr, d_over, round, d_sel, d_nsel, d_counters);
+    RIO_COUNT_LAUNCH(L);
+}
+void launch_classify(const Launch &L, const uint32_t *d_cur, uint64_t n, const uint8_t *d_node_state, uint32_t n_total, uint32_t *d_sel,
+                     unsigned long long *d_nsel, uint8_t *d_dead_flag) {
+    if (!n) return;
+    k_classify<<<grid_for(n, 256, L.sm_count, 8), 256, 0, L.stream>>>(d_cur, n, d_node_state, n_total, d_sel, d_nsel, d_dead_flag);
+    RIO_COUNT_LAUNCH(L);
+}
+void launch_scatter_const(const Launch &L, uint32_t *d_out, const uint32_t *d_sel, uint64_t n_sel, uint32_t v) {
+    if (!n_sel) return;
+    k_scatter_const<<<grid_for(n_sel, 256, L.sm_count, 8), 256, 0, L.stream>>>(d_out, d_sel, n_sel, v);
+    RIO_COUNT_LAUNCH(L);
+}
+void launch_gather_keys(const Launch &L, const uint64_t *d_keys, const uint32_t *d_sel, uint64_t n_sel, uint64_t *d_out_keys, const uint32_t *d_idx,
+                        uint32_t *d_out_idx) {
+    if (!n_sel) return;
+    k_gather_keys<<<grid_for(n_sel, 256, L.sm_count, 8), 256, 0, L.stream>>>(d_keys, d_sel, n_sel, d_out_keys, d_idx, d_out_idx);
+    RIO_COUNT_LAUNCH(L);
+}
+
+}  // namespace rio

@@ -1,0 +1,414 @@
+"""GPU parity tests (run under gpurun): every call goes through the C ABI of librio_cuda.so and is compared with the
+CPU oracle on the same seeded inputs.  Integer / index work is bit-exact; the float-cost path is within 1e-5 relative.
+
+Directory tests restate the reference's own tests against the GPU provider, exactly as a `mod gpu { ... }` block in
+rio-rs/tests/object_placement_backend.rs would.
+"""
+import os
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+NONE = 0xFFFFFFFF
+
+
+@pytest.fixture(scope="module")
+def gp():
+    from rio_rs_b200 import build
+
+    build.build()
+    import rio_rs_b200 as R
+
+    return R
+
+
+def provider(gp, **kw):
+    return gp.GpuObjectPlacement(**kw)
+
+
+# ---- directory semantics: the reference's known-answer tests ------------------------------------------------
+def test_no_placement(gp):
+    """rio-rs/tests/object_placement_backend.rs:11-16"""
+    p = provider(gp)
+    p.prepare()
+    assert p.lookup(gp.ObjectId.new("obj", "1")) is None
+
+
+def test_save_and_load(gp):
+    """rio-rs/tests/object_placement_backend.rs:18-34"""
+    p = provider(gp)
+    p.prepare()
+    p.update(gp.ObjectPlacementItem.new(gp.ObjectId.new("obj", "1"), "0.0.0.0:8888"))
+    assert p.lookup(gp.ObjectId.new("obj", "1")) == "0.0.0.0:8888"
+    p.clean_server("0.0.0.0:8888")
+    assert p.lookup(gp.ObjectId.new("obj", "1")) is None
+
+
+def test_provider_is_clonable(gp):
+    """rio-rs/src/object_placement/local.rs:75-114"""
+    p = provider(gp)
+    q = p.clone()
+    p.update(gp.ObjectPlacementItem.new(gp.ObjectId("test", "1"), "0.0.0.0:80"))
+    assert p.lookup(gp.ObjectId("test", "1")) is not None
+    assert q.lookup(gp.ObjectId("test", "1")) is not None
+    q.clean_server("0.0.0.0:80")
+    assert p.lookup(gp.ObjectId("test", "1")) is None
+    assert q.lookup(gp.ObjectId("test", "1")) is None
+
+
+def test_overwrite_then_clean(gp):
+    """rio-rs/src/object_placement/sqlite.rs:149-193"""
+    p = provider(gp)
+    p.update(gp.ObjectPlacementItem(gp.ObjectId("Test", "1"), "0.0.0.0:5000"))
+    p.update(gp.ObjectPlacementItem(gp.ObjectId("Test", "1"), "0.0.0.0:5001"))
+    assert p.lookup(gp.ObjectId("Test", "1")) == "0.0.0.0:5001"
+    p.clean_server("0.0.0.0:5000")
+    assert p.lookup(gp.ObjectId("Test", "1")) == "0.0.0.0:5001"
+    p.clean_server("0.0.0.0:5001")
+    assert p.lookup(gp.ObjectId("Test", "1")) is None
+    p.clean_server("1.2.3.4:1")  # never-seen address: no-op, not an error
+
+
+def test_update_none_and_remove(gp):
+    """local.rs:34-38 and :60-68"""
+    p = provider(gp)
+    oid = gp.ObjectId("obj", "1")
+    p.update(gp.ObjectPlacementItem(oid, "0.0.0.0:1"))
+    p.update(gp.ObjectPlacementItem(oid, None))
+    assert p.lookup(oid) is None and p.directory_len()[0] == 0
+    p.update(gp.ObjectPlacementItem(oid, "0.0.0.0:1"))
+    p.remove(oid)
+    p.remove(oid)
+    assert p.lookup(oid) is None
+
+
+def test_random_ops_match_directory_model(gp, oracle):
+    """String-level provider vs the LocalObjectPlacement restatement on a random op sequence."""
+    rng = random.Random(3)
+    p, m = provider(gp), oracle.DirectoryModel()
+    addrs = ["10.0.0.%d:5000" % j for j in range(5)]
+    ids = [("T%d" % (i % 3), str(i)) for i in range(40)]
+    for _ in range(600):
+        op = rng.random()
+        t, i = rng.choice(ids)
+        if op < 0.45:
+            a = rng.choice(addrs)
+            p.update(gp.ObjectPlacementItem(gp.ObjectId(t, i), a))
+            m.update(t, i, a)
+        elif op < 0.55:
+            p.remove(gp.ObjectId(t, i))
+            m.remove(t, i)
+        elif op < 0.62:
+            a = rng.choice(addrs)
+            p.clean_server(a)
+            m.clean_server(a)
+        else:
+            assert p.lookup(gp.ObjectId(t, i)) == m.lookup(t, i)
+    for t, i in ids:
+        assert p.lookup(gp.ObjectId(t, i)) == m.lookup(t, i)
+    assert p.directory_len()[0] == len(m)
+
+
+def test_batched_directory_matches_model_with_growth_and_duplicates(gp, oracle):
+    """Batched update/lookup/remove/clean_node vs the model; forces several table growths (initial capacity 1024),
+    and checks the 'last one in array order wins' rule for duplicate keys inside one batch."""
+    p, m = provider(gp, directory_capacity=1024), oracle.DirectoryModel()
+    addrs = ["10.0.0.%d:5000" % j for j in range(7)]
+    nidx = p.set_nodes(addrs)
+    rng = np.random.default_rng(9)
+    n = 50000
+    ids = [("Obj", str(i)) for i in range(n)]
+    keys = p.hash_ids(ids)
+    assert keys.tolist() == [oracle.object_key(t, i) for t, i in ids[:]]  # device FNV == host helper == oracle
+    assert len(set(keys.tolist())) == n
+    for rnd in range(4):
+        sel = rng.integers(0, n, 20000)
+        # duplicates inside the batch on purpose
+        sel[:2000] = sel[2000:4000]
+        tgt = rng.integers(0, len(addrs), len(sel))
+        rm = rng.random(len(sel)) < 0.1
+        idx = np.where(rm, NONE, nidx[tgt]).astype(np.uint32)
+        p.update_many(keys[sel], idx)
+        for s, t, r in zip(sel.tolist(), tgt.tolist(), rm.tolist()):
+            m.update("Obj", str(s), None if r else addrs[t])
+        if rnd == 2:
+            assert p.clean_node(int(nidx[3])) == sum(1 for i in range(n) if m.lookup("Obj", str(i)) == addrs[3])
+            m.clean_server(addrs[3])
+        if rnd == 3:
+            dead = rng.integers(0, n, 3000)
+            p.remove_many(keys[dead])
+            for s in dead.tolist():
+                m.remove("Obj", str(s))
+    got = p.lookup_many(keys)
+    want = []
+    for i in range(n):
+        a = m.lookup("Obj", str(i))
+        want.append(NONE if a is None else int(nidx[addrs.index(a)]))
+    assert got.tolist() == want
+    placed, slots = p.directory_len()
+    assert placed == len(m) and slots >= 2 * placed
+    cnt = p.load_counters()
+    assert cnt.sum() == placed and cnt.tolist() == [want.count(int(j)) for j in nidx]
+    # empty batches are fine
+    p.update_many(np.empty(0, np.uint64), np.empty(0, np.uint32))
+    assert p.lookup_many(np.empty(0, np.uint64)).shape == (0,)
+
+
+# ---- solver: weighted rendezvous, bit-exact --------------------------------------------------------------------
+def _nodes(p, oracle, M, uniform=False):
+    addrs, seeds, w = oracle.synth_nodes(M, uniform=uniform)
+    idx = p.set_nodes(addrs, w)
+    assert idx.tolist() == list(range(M))
+    return addrs, seeds, w
+
+
+@pytest.mark.parametrize("variant", ["2", "1"])
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_c2_weighted_rendezvous_1m_x_64(gp, oracle, seed, variant):
+    """BASELINE.json configs[1]: 1M objects x 64 nodes, weights in [1,16]; both kernel variants."""
+    os.environ["RIO_ASSIGN_VARIANT"] = variant
+    try:
+        p = provider(gp)
+        _, seeds, w = _nodes(p, oracle, 64)
+        keys = oracle.synth_keys(1 << 20, seed)
+        got = p.assign_batch(keys)
+    finally:
+        os.environ.pop("RIO_ASSIGN_VARIANT", None)
+    want = oracle.assign_hrw(keys, seeds, w, threads=8)
+    assert (got == want).all()
+
+
+@pytest.mark.parametrize("variant", ["2", "1"])
+@pytest.mark.parametrize("M,uniform", [(1, True), (2, False), (3, True), (31, False), (33, False), (64, True), (257, False), (1024, False), (1024, True), (1500, False)])
+def test_ragged_node_counts(gp, oracle, M, uniform, variant):
+    os.environ["RIO_ASSIGN_VARIANT"] = variant
+    try:
+        p = provider(gp)
+        _, seeds, w = _nodes(p, oracle, M, uniform)
+        keys = oracle.synth_keys(40013, 2)  # ragged: not a multiple of any tile
+        got = p.assign_batch(keys)
+    finally:
+        os.environ.pop("RIO_ASSIGN_VARIANT", None)
+    assert (got == oracle.assign_hrw(keys, seeds, w, threads=8)).all()
+
+
+def test_many_weight_classes_and_big_weights(gp, oracle):
+    p = provider(gp)
+    addrs, seeds, _ = oracle.synth_nodes(300)
+    rng = np.random.default_rng(4)
+    w = rng.integers(1, 2**31, 300).astype(np.uint32)  # ~300 distinct classes
+    w[7] = 0xFFFFFFFF
+    w[8] = 1
+    p.set_nodes(addrs, w)
+    keys = oracle.synth_keys(30000, 3)
+    assert (p.assign_batch(keys) == oracle.assign_hrw(keys, seeds, w, threads=8)).all()
+
+
+def test_edge_cases_empty_dead_and_raw_keys(gp, oracle):
+    p = provider(gp)
+    addrs, seeds, w = oracle.synth_nodes(16)
+    # no nodes at all -> NONE
+    assert (p.assign_batch(oracle.synth_keys(100, 1)) == NONE).all()
+    w2 = w.copy()
+    w2[::2] = 0  # weight 0 == not live
+    p.set_nodes(addrs, w2)
+    p.node_set_active(1, False)  # set_inactive (peer_to_peer.rs:170-173)
+    w2[1] = 0
+    keys = np.concatenate([np.arange(0, 5000, dtype=np.uint64), np.array([2**64 - 1, 2**64 - 2, 0], dtype=np.uint64)])  # raw, unmixed keys
+    got = p.assign_batch(keys)
+    assert (got == oracle.assign_hrw(keys, seeds, w2)).all()
+    assert p.assign_batch(np.empty(0, np.uint64)).shape == (0,)
+    p.node_set_active(1, True)
+    w2[1] = w[1]
+    assert (p.assign_batch(keys) == oracle.assign_hrw(keys, seeds, w2)).all()
+
+
+def test_golden_vectors_on_gpu(gp):
+    import json
+
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "solver_v1.json")))
+    p = provider(gp)
+    p.set_nodes(g["hrw"]["addresses"], np.array(g["hrw"]["weights"], dtype=np.uint32))
+    keys = np.array([int(k) for k in g["hrw"]["keys"]], dtype=np.uint64)
+    assert p.assign_batch(keys).tolist() == g["hrw"]["idx"]
+    s = p.new_set(len(keys))
+    s.load_keys(keys)
+    passes = s.assign_bounded(0, *g["bounded"]["cap"], g["bounded"]["max_rounds"])
+    assert passes == g["bounded"]["passes"] and s.read().tolist() == g["bounded"]["idx"]
+    assert s.counters().tolist() == g["bounded"]["counts"]
+
+
+# ---- solver: affinity cost, 1e-5 relative ------------------------------------------------------------------------
+@pytest.mark.parametrize("K,M,n", [(16, 1024, 60000), (16, 37, 5001), (8, 64, 3000), (5, 9, 1000)])
+def test_affinity_cost_argmin(gp, oracle, K, M, n):
+    rng = np.random.default_rng(11)
+    fo = rng.uniform(-1, 1, (n, K)).astype(np.float32)
+    fn = np.random.default_rng(13).uniform(-1, 1, (M, K)).astype(np.float32)
+    addrs, _, _ = oracle.synth_nodes(M)
+    w = np.ones(M, dtype=np.uint32)
+    if M > 4:
+        w[3] = 0
+    p = provider(gp)
+    p.set_nodes(addrs, w, fn)
+    got = p.assign_batch(obj_feats=fo)
+    idx, cost, gap = oracle.assign_affinity(fo, fn, w, threads=8)
+    # index must match unless the fp64 top-2 gap is below the tolerance (then either node is accepted);
+    # in every case the fp64 cost of the chosen node is within 1e-5 relative of the optimum
+    tol = 1e-5 * np.abs(cost) + 1e-12
+    mism = got != idx
+    assert (gap[mism] <= tol[mism]).all(), (int(mism.sum()), float(gap[mism].max()) if mism.any() else None)
+    chosen = -(fo.astype(np.float64) * fn.astype(np.float64)[got]).sum(1)
+    assert (np.abs(chosen - cost) <= tol).all()
+    assert (w[got] > 0).all()
+
+
+# ---- resident sets: bounded-load rounds, rebalance storm ----------------------------------------------------------
+def test_set_assign_and_bounded_rounds(gp, oracle):
+    p = provider(gp)
+    addrs, seeds, w = oracle.synth_nodes(64)
+    p.set_nodes(addrs, w)
+    n = 200000
+    s = p.new_set(n)
+    s.synth_keys(0, n, 1)
+    keys = oracle.synth_keys(n, 1)
+    k2, _ = s.read(want_keys=True)
+    assert (k2 == keys).all()  # device key stream == oracle key stream
+    s.assign()
+    want = oracle.assign_hrw(keys, seeds, w, threads=8)
+    assert (s.read() == want).all()
+    assert (s.counters() == oracle.counts(want, 64)).all()
+    for cap in [(5, 4), (101, 100), (1, 1)]:
+        passes = s.assign_bounded(0, cap[0], cap[1], 4)
+        widx, wcnt, wpass = oracle.assign_bounded(keys, seeds, w, cap[0], cap[1], 4, threads=8)
+        assert passes == wpass, cap
+        assert (s.read() == widx).all(), cap
+        assert (s.counters() == wcnt).all(), cap
+
+
+def test_rebalance_storm_matches_fresh_assignment(gp, oracle):
+    """C5 at test scale: 8 join/leave events; after each one the incremental result must equal a from-scratch
+    assignment over the new live set (rendezvous is history-free), and only the minimal set of objects moves."""
+    M0 = 128
+    p = provider(gp)
+    addrs, seeds, w = oracle.synth_nodes(M0 + 4)
+    w_live = w.copy()
+    w_live[M0:] = 0
+    p.set_nodes(addrs[:M0], w[:M0])
+    n = 300000
+    keys = oracle.synth_keys(n, 2)
+    s = p.new_set(n)
+    s.load_keys(keys)
+    s.assign()
+    s.commit()  # directory follows the same events through rio_cuda_rebalance
+    events = [("leave", 17), ("join", M0), ("leave", 3), ("join", M0 + 1), ("leave", 100), ("join", M0 + 2), ("leave", 64), ("join", M0 + 3)]
+    prev = s.read().copy()
+    for ev, j in events:
+        if ev == "leave":
+            p.node_set_active(j, False)
+            w_live[j] = 0
+        else:
+            assert p.node_upsert(addrs[j], int(w[j])) == j
+            w_live[j] = w[j]
+        moved = s.rebalance(ev, j)
+        dmoved = p.rebalance(ev, j)
+        want = oracle.assign_hrw(keys, seeds, w_live, threads=8)
+        got = s.read()
+        assert (got == want).all(), (ev, j)
+        assert moved == int((prev != want).sum()) == dmoved, (ev, j)
+        if ev == "leave":
+            assert (prev[prev != want] == j).all()
+        else:
+            assert (want[prev != want] == j).all()
+        assert (p.lookup_many(keys) == want).all(), (ev, j)
+        assert (s.counters() == oracle.counts(want, M0 + 4)[: len(s.counters())]).all()
+        prev = got.copy()
+
+
+# ---- the per-request policy, batched (service.rs:193-254) -----------------------------------------------------------
+def test_place_batch_self_policy_matches_service_model(gp, oracle):
+    p, m = provider(gp), oracle.DirectoryModel()
+    addrs = ["0.0.0.0:%d" % (5000 + j) for j in range(4)]
+    p.set_nodes(addrs)
+    for a in addrs:
+        ip, port = a.split(":")
+        m.member_push(ip, port, True)
+    ids = [("MockService", str(i)) for i in range(3000)]
+    keys = np.array([oracle.object_key(t, i) for t, i in ids], dtype=np.uint64)
+
+    def both(sel, me):
+        got = p.place_batch(keys[sel], "self", addrs[me])
+        want = [m.get_or_create_placement(addrs[me], *ids[s]) for s in sel]
+        assert [p.node_address(int(g)) for g in got] == want
+
+    both(list(range(0, 2000)), 0)          # unallocated -> claimed by the serving node (service.rs:244-252)
+    both(list(range(1000, 3000)), 1)       # half already owned by node 0 -> kept (-> Redirect upstream)
+    p.node_set_active(0, False)            # owner dies (tests/object_allocation.rs:75-137)
+    m.member_set_active("0.0.0.0", "5000", False)
+    both(list(range(500, 1500)), 2)        # re-placed on the new serving node; clean_server drops node 0's other objects
+    for s in list(range(0, 3000, 7)):
+        a = m.lookup(*ids[s])
+        g = p.lookup(gp.ObjectId(*ids[s]))
+        assert g == a
+    # malformed record (service.rs:213-222): dropped and re-placed
+    p.update(gp.ObjectPlacementItem(gp.ObjectId("MockService", "bad"), "garbage"))
+    m.update("MockService", "bad", "garbage")
+    kb = np.array([oracle.object_key("MockService", "bad")], dtype=np.uint64)
+    assert p.node_address(int(p.place_batch(kb, "self", addrs[3])[0])) == m.get_or_create_placement(addrs[3], "MockService", "bad")
+
+
+def test_place_batch_hrw_policy(gp, oracle):
+    p = provider(gp)
+    addrs, seeds, w = oracle.synth_nodes(32)
+    p.set_nodes(addrs, w)
+    keys = oracle.synth_keys(20000, 3)
+    want = oracle.assign_hrw(keys, seeds, w, threads=4)
+    got = p.place_batch(keys, "hrw")
+    assert (got == want).all() and (p.lookup_many(keys) == want).all()
+    assert (p.place_batch(keys, "hrw") == want).all()  # idempotent: everything already placed on live nodes
+    p.node_set_active(5, False)
+    w2 = w.copy()
+    w2[5] = 0
+    got2 = p.place_batch(keys[:10000], "hrw")
+    want2 = oracle.assign_hrw(keys[:10000], seeds, w2, threads=4)
+    assert (got2 == want2).all()
+    # node 5's objects outside the batch were unassigned by clean_server, the rest is untouched
+    rest = p.lookup_many(keys[10000:])
+    assert (rest[want[10000:] == 5] == NONE).all() and (rest[want[10000:] != 5] == want[10000:][want[10000:] != 5]).all()
+
+
+# ---- full-size properties (BASELINE sizes; the oracle checks a sample) -------------------------------------------------
+def test_full_size_10m_x_1024_properties(gp, oracle):
+    n, M = 10_000_000, 1024
+    p = provider(gp)
+    addrs, seeds, w = oracle.synth_nodes(M)
+    p.set_nodes(addrs, w)
+    s = p.new_set(n)
+    s.synth_keys(0, n, 1)
+    s.assign()
+    idx = s.read()
+    cnt = s.counters()
+    assert cnt.sum() == n and (cnt == np.bincount(idx, minlength=M)).all()
+    # sample of 50k objects against the oracle
+    rng = np.random.default_rng(1)
+    pick = np.sort(rng.choice(n, 50000, replace=False))
+    keys = oracle.synth_keys(n, 1)
+    assert (idx[pick] == oracle.assign_hrw(keys[pick], seeds, w, threads=8)).all()
+    # weights respected: chi-square of counts against w/W
+    e = n * w / w.sum()
+    chi = ((cnt - e) ** 2 / e).sum()
+    assert chi < (M - 1) + 6 * np.sqrt(2 * (M - 1)), chi
+    # leave(17): only node 17's objects move and node 17 ends empty
+    p.node_set_active(17, False)
+    moved = s.rebalance("leave", 17)
+    idx2 = s.read()
+    ch = idx != idx2
+    assert moved == ch.sum() == cnt[17] and (idx[ch] == 17).all() and (idx2 != 17).all()
+    # join(17) back: the exact same objects come back (idempotent round trip)
+    p.node_set_active(17, True)
+    moved2 = s.rebalance("join", 17)
+    assert moved2 == moved and (s.read() == idx).all()
+    # same result through the host-buffer API (H2D/D2H pipelined path)
+    assert (p.assign_batch(keys[:3_000_000]) == idx[:3_000_000]).all()
