@@ -1,0 +1,151 @@
+//! `GpuObjectPlacement` — implements `rio_rs::object_placement::ObjectPlacement`
+//! (rio-rs/src/object_placement/mod.rs:38-56) on top of librio_cuda, so `Server::builder()
+//! .object_placement_provider(GpuObjectPlacement::new(..)?)` (rio-rs/src/server.rs:103-104) works unchanged.
+//!
+//! NOT COMPILED in the authoring image (no cargo/rustc); see rust/README.md.
+use std::ffi::CStr;
+use std::ptr;
+use std::sync::Arc;
+
+use async_trait::async_trait;
+use rio_cuda_sys as sys;
+use rio_rs::errors::ObjectPlacementError;
+use rio_rs::object_placement::{ObjectPlacement, ObjectPlacementItem};
+use rio_rs::ObjectId;
+
+/// Owns the engine handle; dropped (rio_cuda_destroy) when the last provider clone goes away.
+struct Engine(*mut sys::rio_placement);
+// The C library is internally synchronised per handle (include/rio_cuda.h "Conventions").
+unsafe impl Send for Engine {}
+unsafe impl Sync for Engine {}
+impl Drop for Engine {
+    fn drop(&mut self) {
+        unsafe { sys::rio_cuda_destroy(self.0) }
+    }
+}
+
+/// Cheap to clone; clones share state like `LocalObjectPlacement` (local.rs:12-18, test local.rs:75-114).
+#[derive(Clone)]
+pub struct GpuObjectPlacement {
+    engine: Arc<Engine>,
+}
+
+impl std::fmt::Debug for GpuObjectPlacement {
+    fn fmt(&self, f: &mut std::fmt::Formatter<'_>) -> std::fmt::Result {
+        f.debug_struct("GpuObjectPlacement").finish()
+    }
+}
+
+fn check(h: *mut sys::rio_placement, st: sys::rio_status) -> Result<(), ObjectPlacementError> {
+    if st == sys::RIO_OK {
+        return Ok(());
+    }
+    let msg = unsafe {
+        let p = sys::rio_cuda_last_error(h);
+        if p.is_null() { String::new() } else { CStr::from_ptr(p).to_string_lossy().into_owned() }
+    };
+    Err(if st == sys::RIO_ERR_UPSTREAM { ObjectPlacementError::Upstream(msg) } else { ObjectPlacementError::Unknown(msg) })
+}
+
+impl GpuObjectPlacement {
+    pub fn new(device: i32) -> Result<Self, ObjectPlacementError> {
+        let cfg = sys::rio_config { struct_size: std::mem::size_of::<sys::rio_config>() as u32, device, ..Default::default() };
+        let mut h = ptr::null_mut();
+        check(ptr::null_mut(), unsafe { sys::rio_cuda_create(&cfg, &mut h) })?;
+        Ok(Self { engine: Arc::new(Engine(h)) })
+    }
+    fn h(&self) -> *mut sys::rio_placement {
+        self.engine.0
+    }
+
+    /// The live node set as seen by MembershipStorage::active_members (storage/mod.rs:95-99).
+    pub fn set_nodes(&self, addresses: &[String], weights: Option<&[u32]>) -> Result<Vec<u32>, ObjectPlacementError> {
+        let c: Vec<std::ffi::CString> = addresses.iter().map(|a| std::ffi::CString::new(a.as_str()).unwrap()).collect();
+        let p: Vec<*const libc::c_char> = c.iter().map(|s| s.as_ptr()).collect();
+        let mut out = vec![0u32; addresses.len()];
+        check(self.h(), unsafe {
+            sys::rio_cuda_set_nodes(self.h(), p.as_ptr(), weights.map_or(ptr::null(), |w| w.as_ptr()), ptr::null(), p.len() as u32, 0, out.as_mut_ptr())
+        })?;
+        Ok(out)
+    }
+
+    /// Batched resolve: Service::get_or_create_placement (service.rs:193-254) for many ids in one launch.
+    pub fn place_batch(&self, keys: &[u64], self_idx: Option<u32>) -> Result<Vec<u32>, ObjectPlacementError> {
+        let mut out = vec![sys::RIO_NONE; keys.len()];
+        let (policy, me) = match self_idx { Some(i) => (sys::RIO_PLACE_SELF, i), None => (sys::RIO_PLACE_HRW, 0) };
+        check(self.h(), unsafe { sys::rio_cuda_place_batch(self.h(), keys.as_ptr(), keys.len(), policy, me, out.as_mut_ptr()) })?;
+        Ok(out)
+    }
+    pub fn lookup_many(&self, keys: &[u64]) -> Result<Vec<u32>, ObjectPlacementError> {
+        let mut out = vec![sys::RIO_NONE; keys.len()];
+        check(self.h(), unsafe { sys::rio_cuda_lookup_batch(self.h(), keys.as_ptr(), keys.len(), out.as_mut_ptr()) })?;
+        Ok(out)
+    }
+    pub fn update_many(&self, keys: &[u64], idx: &[u32]) -> Result<(), ObjectPlacementError> {
+        assert_eq!(keys.len(), idx.len());
+        check(self.h(), unsafe { sys::rio_cuda_upsert_batch(self.h(), keys.as_ptr(), idx.as_ptr(), keys.len()) })
+    }
+    pub fn assign_batch(&self, keys: &[u64]) -> Result<Vec<u32>, ObjectPlacementError> {
+        let mut out = vec![sys::RIO_NONE; keys.len()];
+        check(self.h(), unsafe { sys::rio_cuda_assign_batch(self.h(), keys.as_ptr(), ptr::null(), keys.len(), out.as_mut_ptr()) })?;
+        Ok(out)
+    }
+    /// Eager re-placement after a membership event (beside peer_to_peer.rs:170-191).
+    pub fn rebalance(&self, join: bool, node_idx: u32) -> Result<u64, ObjectPlacementError> {
+        let mut moved = 0u64;
+        check(self.h(), unsafe { sys::rio_cuda_rebalance(self.h(), if join { sys::RIO_EV_JOIN } else { sys::RIO_EV_LEAVE }, node_idx, &mut moved) })?;
+        Ok(moved)
+    }
+    pub fn object_key(id: &ObjectId) -> u64 {
+        unsafe { sys::rio_cuda_object_key(id.0.as_ptr() as *const _, id.0.len(), id.1.as_ptr() as *const _, id.1.len()) }
+    }
+}
+
+/// FFI calls block for tens of microseconds: keep them off the async workers (SURVEY section 7 hard part 5).
+async fn blocking<T: Send + 'static>(f: impl FnOnce() -> Result<T, ObjectPlacementError> + Send + 'static) -> Result<T, ObjectPlacementError> {
+    tokio::task::spawn_blocking(f).await.map_err(|e| ObjectPlacementError::Unknown(e.to_string()))?
+}
+
+#[async_trait]
+impl ObjectPlacement for GpuObjectPlacement {
+    // prepare(): default Ok(()) (mod.rs:41-43); the engine was created in new().
+
+    async fn update(&self, item: ObjectPlacementItem) -> Result<(), ObjectPlacementError> {
+        let this = self.clone();
+        blocking(move || {
+            let (t, i) = (&item.object_id.0, &item.object_id.1);
+            let (ap, al) = match &item.server_address { Some(a) => (a.as_ptr() as *const libc::c_char, a.len()), None => (ptr::null(), 0) };
+            check(this.h(), unsafe { sys::rio_cuda_update_str(this.h(), t.as_ptr() as *const _, t.len(), i.as_ptr() as *const _, i.len(), ap, al) })
+        })
+        .await
+    }
+
+    async fn lookup(&self, object_id: &ObjectId) -> Result<Option<String>, ObjectPlacementError> {
+        let this = self.clone();
+        let (t, i) = (object_id.0.clone(), object_id.1.clone());
+        blocking(move || {
+            let mut buf = vec![0u8; 256];
+            let mut len: libc::size_t = 0;
+            check(this.h(), unsafe {
+                sys::rio_cuda_lookup_str(this.h(), t.as_ptr() as *const _, t.len(), i.as_ptr() as *const _, i.len(), buf.as_mut_ptr() as *mut _, buf.len(), &mut len)
+            })?;
+            if len == usize::MAX {
+                return Ok(None); // missing id is Ok(None), not an error (tests/object_placement_backend.rs:14-15)
+            }
+            buf.truncate(len.min(256));
+            Ok(Some(String::from_utf8_lossy(&buf).into_owned()))
+        })
+        .await
+    }
+
+    async fn clean_server(&self, address: String) -> Result<(), ObjectPlacementError> {
+        let this = self.clone();
+        blocking(move || check(this.h(), unsafe { sys::rio_cuda_clean_server_str(this.h(), address.as_ptr() as *const _, address.len()) })).await
+    }
+
+    async fn remove(&self, object_id: &ObjectId) -> Result<(), ObjectPlacementError> {
+        let this = self.clone();
+        let (t, i) = (object_id.0.clone(), object_id.1.clone());
+        blocking(move || check(this.h(), unsafe { sys::rio_cuda_remove_str(this.h(), t.as_ptr() as *const _, t.len(), i.as_ptr() as *const _, i.len()) })).await
+    }
+}

@@ -1,0 +1,102 @@
+//! Raw bindings for `include/rio_cuda.h` (ABI version 1).  One declaration per exported symbol.
+#![allow(non_camel_case_types)]
+use libc::{c_char, c_void, size_t};
+
+pub type rio_status = i32;
+pub const RIO_OK: rio_status = 0;
+pub const RIO_ERR_UPSTREAM: rio_status = -1; // -> ObjectPlacementError::Upstream
+pub const RIO_ERR_UNKNOWN: rio_status = -2; // -> ObjectPlacementError::Unknown
+pub const RIO_NONE: u32 = 0xFFFF_FFFF;
+pub const RIO_PLACE_SELF: u32 = 0;
+pub const RIO_PLACE_HRW: u32 = 1;
+pub const RIO_EV_JOIN: u32 = 1;
+pub const RIO_EV_LEAVE: u32 = 2;
+pub const RIO_COMM_ID_BYTES: usize = 128;
+
+#[repr(C)]
+pub struct rio_placement {
+    _private: [u8; 0],
+}
+#[repr(C)]
+pub struct rio_objset {
+    _private: [u8; 0],
+}
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct rio_config {
+    pub struct_size: u32,
+    pub device: i32,
+    pub directory_capacity: u64,
+    pub flags: u32,
+    pub reserved: u32,
+}
+
+extern "C" {
+    pub fn rio_cuda_abi_version() -> u32;
+    pub fn rio_cuda_create(cfg: *const rio_config, out: *mut *mut rio_placement) -> rio_status;
+    pub fn rio_cuda_destroy(h: *mut rio_placement);
+    pub fn rio_cuda_last_error(h: *mut rio_placement) -> *const c_char;
+    pub fn rio_cuda_sync(h: *mut rio_placement) -> rio_status;
+    pub fn rio_cuda_device_info(h: *mut rio_placement, device: *mut i32, sm_count: *mut i32, hbm_bytes: *mut u64, name_buf: *mut c_char, name_cap: size_t) -> rio_status;
+
+    pub fn rio_cuda_object_key(ty: *const c_char, ty_len: size_t, id: *const c_char, id_len: size_t) -> u64;
+    pub fn rio_cuda_node_seed(address: *const c_char, len: size_t) -> u64;
+    pub fn rio_cuda_hash_ids(h: *mut rio_placement, packed: *const c_char, offsets: *const u64, n: size_t, out_keys: *mut u64) -> rio_status;
+
+    pub fn rio_cuda_set_nodes(h: *mut rio_placement, addrs: *const *const c_char, weights: *const u32, feats: *const f32, m: u32, k: u32, out_idx: *mut u32) -> rio_status;
+    pub fn rio_cuda_node_upsert(h: *mut rio_placement, address: *const c_char, weight: u32, feat: *const f32, k: u32, out_idx: *mut u32) -> rio_status;
+    pub fn rio_cuda_node_set_active(h: *mut rio_placement, idx: u32, active: i32) -> rio_status;
+    pub fn rio_cuda_node_index(h: *mut rio_placement, address: *const c_char, out_idx: *mut u32) -> rio_status;
+    pub fn rio_cuda_node_address(h: *mut rio_placement, idx: u32, buf: *mut c_char, cap: size_t, out_len: *mut size_t) -> rio_status;
+    pub fn rio_cuda_node_count(h: *mut rio_placement, out_total: *mut u32, out_live: *mut u32) -> rio_status;
+
+    pub fn rio_cuda_lookup_batch(h: *mut rio_placement, keys: *const u64, n: size_t, out_idx: *mut u32) -> rio_status;
+    pub fn rio_cuda_upsert_batch(h: *mut rio_placement, keys: *const u64, idx: *const u32, n: size_t) -> rio_status;
+    pub fn rio_cuda_remove_batch(h: *mut rio_placement, keys: *const u64, n: size_t) -> rio_status;
+    pub fn rio_cuda_clean_node(h: *mut rio_placement, idx: u32, out_removed: *mut u64) -> rio_status;
+    pub fn rio_cuda_directory_len(h: *mut rio_placement, out_placed: *mut u64, out_slots: *mut u64) -> rio_status;
+    pub fn rio_cuda_directory_reserve(h: *mut rio_placement, n_more: u64) -> rio_status;
+
+    pub fn rio_cuda_assign_batch(h: *mut rio_placement, keys: *const u64, obj_feats: *const f32, n: size_t, out_idx: *mut u32) -> rio_status;
+    pub fn rio_cuda_place_batch(h: *mut rio_placement, keys: *const u64, n: size_t, policy: u32, self_idx: u32, out_idx: *mut u32) -> rio_status;
+    pub fn rio_cuda_rebalance(h: *mut rio_placement, event: u32, idx: u32, out_moved: *mut u64) -> rio_status;
+    pub fn rio_cuda_load_counters(h: *mut rio_placement, out: *mut u32, cap: u32) -> rio_status;
+
+    pub fn rio_cuda_set_create(h: *mut rio_placement, capacity: u64, out: *mut *mut rio_objset) -> rio_status;
+    pub fn rio_cuda_set_destroy(s: *mut rio_objset);
+    pub fn rio_cuda_set_load_keys(s: *mut rio_objset, keys: *const u64, n: u64) -> rio_status;
+    pub fn rio_cuda_set_synth_keys(s: *mut rio_objset, first: u64, n: u64, seed: u64) -> rio_status;
+    pub fn rio_cuda_set_load_feats(s: *mut rio_objset, feats: *const f32, k: u32) -> rio_status;
+    pub fn rio_cuda_set_assign(s: *mut rio_objset, use_affinity: u32) -> rio_status;
+    pub fn rio_cuda_set_assign_bounded(s: *mut rio_objset, n_total: u64, cap_num: u32, cap_den: u32, max_rounds: u32, out_passes: *mut u32) -> rio_status;
+    pub fn rio_cuda_set_rebalance(s: *mut rio_objset, event: u32, idx: u32, out_moved: *mut u64) -> rio_status;
+    pub fn rio_cuda_set_counters(s: *mut rio_objset, out: *mut u32, cap: u32) -> rio_status;
+    pub fn rio_cuda_set_read(s: *mut rio_objset, first: u64, n: u64, out_keys: *mut u64, out_idx: *mut u32) -> rio_status;
+    pub fn rio_cuda_set_size(s: *mut rio_objset, out_n: *mut u64) -> rio_status;
+    pub fn rio_cuda_set_commit(s: *mut rio_objset) -> rio_status;
+
+    pub fn rio_cuda_comm_unique_id(out_id: *mut u8) -> rio_status;
+    pub fn rio_cuda_comm_init(h: *mut rio_placement, rank: i32, world: i32, id: *const u8) -> rio_status;
+    pub fn rio_cuda_comm_info(h: *mut rio_placement, rank: *mut i32, world: *mut i32) -> rio_status;
+    pub fn rio_cuda_comm_sum_counters(h: *mut rio_placement, inout: *mut u32, m: u32) -> rio_status;
+
+    pub fn rio_cuda_dev_alloc(h: *mut rio_placement, bytes: size_t, out_dev: *mut *mut c_void) -> rio_status;
+    pub fn rio_cuda_dev_free(h: *mut rio_placement, dev: *mut c_void) -> rio_status;
+    pub fn rio_cuda_host_alloc(h: *mut rio_placement, bytes: size_t, out_pinned: *mut *mut c_void) -> rio_status;
+    pub fn rio_cuda_host_free(h: *mut rio_placement, pinned: *mut c_void) -> rio_status;
+    pub fn rio_cuda_memcpy_h2d(h: *mut rio_placement, dev: *mut c_void, host: *const c_void, bytes: size_t) -> rio_status;
+    pub fn rio_cuda_memcpy_d2h(h: *mut rio_placement, host: *mut c_void, dev: *const c_void, bytes: size_t) -> rio_status;
+    pub fn rio_cuda_assign_batch_dev(h: *mut rio_placement, d_keys: *const u64, d_obj_feats: *const f32, n: size_t, d_out_idx: *mut u32) -> rio_status;
+    pub fn rio_cuda_lookup_batch_dev(h: *mut rio_placement, d_keys: *const u64, n: size_t, d_out_idx: *mut u32) -> rio_status;
+    pub fn rio_cuda_upsert_batch_dev(h: *mut rio_placement, d_keys: *const u64, d_idx: *const u32, n: size_t) -> rio_status;
+    pub fn rio_cuda_flush_l2(h: *mut rio_placement) -> rio_status;
+    pub fn rio_cuda_event_record(h: *mut rio_placement, slot: u32) -> rio_status;
+    pub fn rio_cuda_event_elapsed_ms(h: *mut rio_placement, a: u32, b: u32, out_ms: *mut f32) -> rio_status;
+    pub fn rio_cuda_bench_mix_rate(h: *mut rio_placement, iters: u32, out_pairs_per_s: *mut f64) -> rio_status;
+    pub fn rio_cuda_launch_count(h: *mut rio_placement, out: *mut u64) -> rio_status;
+
+    pub fn rio_cuda_update_str(h: *mut rio_placement, ty: *const c_char, ty_len: size_t, id: *const c_char, id_len: size_t, address: *const c_char, address_len: size_t) -> rio_status;
+    pub fn rio_cuda_lookup_str(h: *mut rio_placement, ty: *const c_char, ty_len: size_t, id: *const c_char, id_len: size_t, buf: *mut c_char, cap: size_t, out_len: *mut size_t) -> rio_status;
+    pub fn rio_cuda_clean_server_str(h: *mut rio_placement, address: *const c_char, address_len: size_t) -> rio_status;
+    pub fn rio_cuda_remove_str(h: *mut rio_placement, ty: *const c_char, ty_len: size_t, id: *const c_char, id_len: size_t) -> rio_status;
+}
