@@ -114,13 +114,15 @@ static inline orc_objh obj_hash(uint64_t key) {
     orc_objh o; o.b = (uint32_t)(h >> 32) | 1u; o.ab = a * o.b; return o;
 }
 
+/* u = ((p ^ (p >> 15) ^ s1) * C1 + s2) mod 2^32 with p = (s0*b + ab) mod 2^32;
+ * (s0, s1) = (lo32, hi32) of the node seed, s2 = lo32(mix64(seed ^ SALT_NODE2)) */
+static inline uint32_t pair_u(orc_objh o, uint64_t seed, uint32_t s2) {
+    uint32_t p = (uint32_t)seed * o.b + o.ab;
+    uint32_t q = p ^ (p >> 15) ^ (uint32_t)(seed >> 32);
+    return q * PAIR_C1 + s2;
+}
 uint32_t orc_pair_hash(uint64_t key, uint64_t node_seed) {
-    orc_objh o = obj_hash(key);
-    uint32_t s0 = (uint32_t)node_seed;
-    uint64_t s2 = orc_mix64(node_seed ^ SALT_NODE2);
-    uint32_t p = s0 * o.b + o.ab;
-    uint64_t t = (uint64_t)p * PAIR_C1 + s2;
-    return (uint32_t)t ^ (uint32_t)(t >> 32);
+    return pair_u(obj_hash(key), node_seed, (uint32_t)orc_mix64(node_seed ^ SALT_NODE2));
 }
 
 uint32_t orc_inv_weight(uint32_t w) { return w ? 0xFFFFFFFFu / w : 0u; }
@@ -134,9 +136,7 @@ static uint32_t hrw_one(uint64_t key, const uint64_t *seed, const uint64_t *seed
     for (uint32_t j = 0; j < M; j++) {
         if (!invw[j]) continue;
         if (mask && (mask[j >> 5] >> (j & 31) & 1u)) continue;
-        uint32_t p = (uint32_t)seed[j] * o.b + o.ab;
-        uint64_t t = (uint64_t)p * PAIR_C1 + seed2[j];
-        uint32_t u = (uint32_t)t ^ (uint32_t)(t >> 32);
+        uint32_t u = pair_u(o, seed[j], (uint32_t)seed2[j]);
         uint64_t sc = (uint64_t)orc_elog(u) * invw[j];
         if (bj == ORC_NONE || sc < best || (sc == best && u > bu)) { best = sc; bu = u; bj = j; }
     }

@@ -131,7 +131,8 @@ struct rio_placement {
     uint32_t K = 0;
     bool tab_dirty = true;
     TabBufs tabs, tabs_masked;
-    DevBuf d_node_state, d_live, d_fnode;
+    DevBuf d_node_state, d_live, d_fnode, d_fnode_c, d_nidx_map;
+    uint32_t aff_live = 0, aff_pad = 0;   // compacted live-node operands of the tcgen05 affinity kernel
 
     DirDev dir{};
     uint64_t dir_cap = 0;
@@ -216,7 +217,7 @@ void build_tab(rio_placement *h, TabBufs &tb, const std::vector<uint8_t> *closed
     std::vector<ClassRec> classes;
     for (size_t q = 0; q < live.size(); q++) {
         const NodeInfo &ni = h->nodes[live[q].idx];
-        recs[q] = NodeRec{(uint32_t)ni.seed, live[q].idx, (uint32_t)ni.seed2, (uint32_t)(ni.seed2 >> 32)};
+        recs[q] = NodeRec{(uint32_t)ni.seed, live[q].idx, (uint32_t)(ni.seed >> 32), (uint32_t)ni.seed2};
         if (q == 0 || live[q].invw != live[q - 1].invw) classes.push_back(ClassRec{(uint32_t)q, live[q].invw});
     }
     const uint32_t n_classes = (uint32_t)classes.size();
@@ -226,7 +227,7 @@ void build_tab(rio_placement *h, TabBufs &tb, const std::vector<uint8_t> *closed
     for (uint32_t j = 0; j < n_total; j++) {
         const NodeInfo &ni = h->nodes[j];
         const bool lv = ni.live() && !(closed && (*closed)[j]);
-        by_idx[j] = make_uint4((uint32_t)ni.seed, lv ? inv_weight(ni.weight) : 0u, (uint32_t)ni.seed2, (uint32_t)(ni.seed2 >> 32));
+        by_idx[j] = make_uint4((uint32_t)ni.seed, lv ? inv_weight(ni.weight) : 0u, (uint32_t)(ni.seed >> 32), (uint32_t)ni.seed2);
     }
     cudaStream_t st = h->stream;
     tb.recs.ensure(recs.size() * sizeof(NodeRec), st);
@@ -264,6 +265,23 @@ void ensure_tab(rio_placement *h) {
     CUDA_TRY(cudaMemcpyAsync(h->d_node_state.p, state.data(), state.size(), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(h->d_live.p, live.data(), live.size() * 4, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(h->d_fnode.p, fnode.data(), fnode.size() * 4, cudaMemcpyHostToDevice, st));
+    // compacted live nodes (node-index order) for the tensor-core affinity kernel, zero padded to the node tile
+    h->aff_live = h->aff_pad = 0;
+    if (h->K == 16) {
+        std::vector<uint32_t> map;
+        for (uint32_t j = 0; j < n_total; j++) if (h->nodes[j].live()) map.push_back(j);
+        const uint32_t nl = (uint32_t)map.size();
+        const uint32_t pad = nl <= 64 ? 64 : (nl + 255) / 256 * 256;
+        std::vector<float> fc((size_t)pad * 16, 0.f);
+        for (uint32_t q = 0; q < nl; q++) if (h->nodes[map[q]].feat.size() == 16) std::copy(h->nodes[map[q]].feat.begin(), h->nodes[map[q]].feat.end(), fc.begin() + (size_t)q * 16);
+        map.resize(pad, kNone);
+        h->d_fnode_c.ensure(fc.size() * 4, st);
+        h->d_nidx_map.ensure(map.size() * 4, st);
+        CUDA_TRY(cudaMemcpyAsync(h->d_fnode_c.p, fc.data(), fc.size() * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(h->d_nidx_map.p, map.data(), map.size() * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        h->aff_live = nl; h->aff_pad = pad;
+    }
     CUDA_TRY(cudaStreamSynchronize(st));
     h->tab_dirty = false;
 }
@@ -320,6 +338,21 @@ void exchange_counters(rio_placement *h, const uint32_t *d_local, uint32_t *d_gl
     launch_sum_gathered(h->L(), h->s_gather.as<uint32_t>(), (uint32_t)h->world, M, d_global);
 }
 
+// affinity dispatch: tcgen05 kernel for K == 16 (unless RIO_AFFINITY_VARIANT=ffma or the node set does not fit), else CUDA cores
+void run_affinity(rio_placement *h, const float *d_fobj, uint64_t n, uint32_t *d_out_idx, float *d_out_cost, uint32_t *d_counters) {
+    if (!n) return;
+    const char *v = getenv("RIO_AFFINITY_VARIANT");
+    const bool want_umma = !(v && v[0] == 'f');
+    if (!h->aff_live && h->K == 16 && h->tabs.tab.n_live == 0) { launch_fill_u32(h->L(), d_out_idx, n, kNone); return; }
+    if (want_umma && h->K == 16 && h->aff_live && h->aff_pad <= affinity_umma_max_nodes()) {
+        const char *sw = getenv("RIO_UMMA_SWAP");
+        if (launch_assign_affinity_umma(h->L(), d_fobj, n, h->d_fnode_c.as<float>(), h->d_nidx_map.as<uint32_t>(), h->aff_live, h->aff_pad, d_out_idx, d_out_cost,
+                                        d_counters, sw && sw[0] == '1'))
+            return;
+    }
+    launch_assign_affinity(h->L(), d_fobj, n, h->d_fnode.as<float>(), h->d_live.as<uint32_t>(), h->tabs.tab.n_total, h->K, d_out_idx, d_out_cost, d_counters);
+}
+
 uint32_t capacity_of(uint64_t n_total, uint32_t w, uint64_t w_sum, uint32_t num, uint32_t den) {
     if (!w || !w_sum || !den) return 0;
     unsigned __int128 a = (unsigned __int128)num * n_total * w, b = (unsigned __int128)den * w_sum;
@@ -345,8 +378,7 @@ void assign_host_pipelined(rio_placement *h, const uint64_t *keys, const float *
         CUDA_TRY(cudaEventRecord(h->ev_pipe[1], h->h2d_stream));
         CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_pipe[1], 0));
         if (feats)
-            launch_assign_affinity(h->L(), h->s_feats.as<float>() + lo * h->K, m, h->d_fnode.as<float>(), h->d_live.as<uint32_t>(), h->tabs.tab.n_total, h->K,
-                                   h->s_idx.as<uint32_t>() + lo, nullptr, nullptr);
+            run_affinity(h, h->s_feats.as<float>() + lo * h->K, m, h->s_idx.as<uint32_t>() + lo, nullptr, nullptr);
         else
             launch_assign_hrw(h->L(), h->s_keys.as<uint64_t>() + lo, m, h->tabs.tab, h->s_idx.as<uint32_t>() + lo, nullptr, nullptr, 0);
         CUDA_TRY(cudaEventRecord(h->ev_pipe[2], h->stream));
@@ -464,7 +496,7 @@ void rio_cuda_destroy(rio_placement *h) {
     cudaStreamSynchronize(h->stream);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     DevBuf *bufs[] = {&h->tabs.recs, &h->tabs.classes, &h->tabs.by_idx, &h->tabs_masked.recs, &h->tabs_masked.classes, &h->tabs_masked.by_idx,
-                      &h->d_node_state, &h->d_live, &h->d_fnode, &h->s_keys, &h->s_idx, &h->s_idx2, &h->s_sel, &h->s_slots, &h->s_keys2, &h->s_feats,
+                      &h->d_node_state, &h->d_live, &h->d_fnode, &h->d_fnode_c, &h->d_nidx_map, &h->s_keys, &h->s_idx, &h->s_idx2, &h->s_sel, &h->s_slots, &h->s_keys2, &h->s_feats,
                       &h->s_packed, &h->s_offsets, &h->s_cost, &h->s_misc, &h->s_flush, &h->s_gather};
     for (DevBuf *b : bufs) b->release(h->stream);
     if (h->dir.slots) cudaFreeAsync(h->dir.slots, h->stream);
@@ -700,7 +732,7 @@ rio_status rio_cuda_assign_batch_dev(rio_placement *h, const uint64_t *d_keys, c
         ensure_tab(h);
         if (d_obj_feats) {
             REQUIRE(h->K > 0, "assign with object features needs node features");
-            launch_assign_affinity(h->L(), d_obj_feats, n, h->d_fnode.as<float>(), h->d_live.as<uint32_t>(), h->tabs.tab.n_total, h->K, d_out_idx, nullptr, nullptr);
+            run_affinity(h, d_obj_feats, n, d_out_idx, nullptr, nullptr);
         } else {
             launch_assign_hrw(h->L(), d_keys, n, h->tabs.tab, d_out_idx, nullptr, nullptr, 0);
         }
@@ -856,8 +888,7 @@ rio_status rio_cuda_set_assign(rio_objset *s, uint32_t use_affinity) {
         CUDA_TRY(cudaMemsetAsync(s->counters.p, 0, (size_t)std::max(s->counters_n, 1u) * 4, h->stream));
         if (use_affinity) {
             REQUIRE(s->K > 0 && s->K == h->K, "set features / node features missing or of different K");
-            launch_assign_affinity(h->L(), s->feats.as<float>(), s->n, h->d_fnode.as<float>(), h->d_live.as<uint32_t>(), h->tabs.tab.n_total, h->K,
-                                   s->idx.as<uint32_t>(), nullptr, s->counters.as<uint32_t>());
+            run_affinity(h, s->feats.as<float>(), s->n, s->idx.as<uint32_t>(), nullptr, s->counters.as<uint32_t>());
         } else {
             launch_assign_hrw(h->L(), s->keys.as<uint64_t>(), s->n, h->tabs.tab, s->idx.as<uint32_t>(), s->counters.as<uint32_t>(), nullptr, 0);
         }

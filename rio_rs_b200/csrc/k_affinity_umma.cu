@@ -1,0 +1,312 @@
+// k_affinity_umma.cu -- affinity-cost placement on the 5th-gen tensor cores (tcgen05 + TMEM), K = 16.
+//
+//   cost_ij = -sum_k Fobj[i,k] * Fnode[j,k]   ->  per-object argmin over the live nodes   
+//
+// This is the one dense contraction on the path, so it is the one place tensor cores are used.  fp32 inputs are split
+// on the fly into three bf16 pieces (a = a_h + a_m + a_l exactly) and the product is rebuilt from six cross terms
+// (hh, hm, mh, mm, hl, lh; the dropped terms are <= 2^-24 relative), each term ONE tcgen05.mma (M=128 objects x
+// N=NT nodes x K=16) accumulating in fp32 in TMEM.  Nothing is materialised in HBM: the N x M grid lives only in TMEM.
+//
+// Warp roles (288 threads, one CTA per SM, persistent over 128-object row blocks):
+//   warps 0-3  producers : load 128 object rows (fp32, coalesced), split to bf16 h/m/l, store the three K-major
+//                          16-byte-interleaved operand blocks into shared memory, fence.proxy.async, arrive a_full
+//   warp  8    MMA issuer: one lane issues 6 tcgen05.mma per node tile into one of two TMEM accumulators,
+//                          tcgen05.commit -> tmem_full (and -> a_empty after the last tile of the row block)
+//   warps 4-7  epilogue  : tcgen05.ld 32 columns at a time, 3-input max over groups of 8 columns, keep (best value,
+//                          best group); arrive tmem_empty; after the last tile re-evaluate the 8 candidates of the winning
+//                          group in fp32 (same fmaf order as the CUDA-core kernel) to get the index and the exact cost.
+// Node operands (3 bf16 blocks, 96 B per node) stay resident in shared memory for the whole kernel.
+#include "kernels.cuh"
+#include "spec.cuh"
+
+#include <cuda_bf16.h>
+
+namespace rio {
+
+namespace {
+
+constexpr int kUmmaThreads = 288;
+constexpr int kRows = 128;          // objects per row block == UMMA M
+constexpr int kStages = 2;          // A-operand stages
+constexpr uint32_t kABlockBytes = kRows * 32;            // one bf16 term of a row block: [2 k-chunks][128 rows][16 B]
+constexpr uint32_t kAStageBytes = 3 * kABlockBytes;      // h, m, l
+constexpr uint32_t kBarBytes = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+                   "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+                   "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, no-swizzle ("interleave") shared-memory operand descriptor: 8-row x 16-byte core matrices,
+// LBO = byte distance between the two 16-byte K chunks, SBO = byte distance between 8-row groups.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) |
+           (1ull << 46);   // descriptor version 1 (Blackwell), base offset 0, SWIZZLE_NONE
+}
+
+// fp32 -> three bf16 pieces with a == h + m + l exactly
+__device__ __forceinline__ void split3(float a, __nv_bfloat16 &h, __nv_bfloat16 &m, __nv_bfloat16 &l) {
+    h = __float2bfloat16_rn(a);
+    const float r1 = a - __bfloat162float(h);
+    m = __float2bfloat16_rn(r1);
+    l = __float2bfloat16_rn(r1 - __bfloat162float(m));
+}
+__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 lo, __nv_bfloat16 hi) {
+    return (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
+}
+
+// Split one fp32 row of 16 features and store it as row `r` of the three operand blocks at `base`
+// (block x at base + x*block_bytes; inside a block: [k-chunk][row][16 B], chunk stride = chunk_stride bytes).
+__device__ __forceinline__ void store_row_split(unsigned char *base, uint32_t block_bytes, uint32_t chunk_stride, uint32_t r, const float (&f)[16]) {
+    __nv_bfloat16 h[16], m[16], l[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) split3(f[k], h[k], m[k], l[k]);
+#pragma unroll
+    for (int kc = 0; kc < 2; kc++) {
+        uint4 vh = make_uint4(pack2(h[kc * 8 + 0], h[kc * 8 + 1]), pack2(h[kc * 8 + 2], h[kc * 8 + 3]), pack2(h[kc * 8 + 4], h[kc * 8 + 5]), pack2(h[kc * 8 + 6], h[kc * 8 + 7]));
+        uint4 vm = make_uint4(pack2(m[kc * 8 + 0], m[kc * 8 + 1]), pack2(m[kc * 8 + 2], m[kc * 8 + 3]), pack2(m[kc * 8 + 4], m[kc * 8 + 5]), pack2(m[kc * 8 + 6], m[kc * 8 + 7]));
+        uint4 vl = make_uint4(pack2(l[kc * 8 + 0], l[kc * 8 + 1]), pack2(l[kc * 8 + 2], l[kc * 8 + 3]), pack2(l[kc * 8 + 4], l[kc * 8 + 5]), pack2(l[kc * 8 + 6], l[kc * 8 + 7]));
+        const uint32_t off = kc * chunk_stride + r * 16;
+        *reinterpret_cast<uint4 *>(base + 0 * block_bytes + off) = vh;
+        *reinterpret_cast<uint4 *>(base + 1 * block_bytes + off) = vm;
+        *reinterpret_cast<uint4 *>(base + 2 * block_bytes + off) = vl;
+    }
+}
+
+__device__ __forceinline__ float max3f(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
+struct UmmaParams {
+    const float *fobj;        // n x 16
+    uint64_t n;
+    const float *fnode_c;     // m_pad x 16 fp32, live nodes compacted in node-index order, zero padded
+    const uint32_t *nidx_map; // compacted position -> interned node index
+    uint32_t n_live, m_pad;
+    uint32_t *out_idx;
+    float *out_cost;          // nullable
+    uint32_t *counters;       // nullable
+    uint32_t lbo_a, sbo_a, lbo_b, sbo_b;   // descriptor strides in bytes (passed from the host so a probe run can flip them)
+};
+
+template <int NT>
+__global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t *a_full = reinterpret_cast<uint64_t *>(smem);         // [kStages]
+    uint64_t *a_empty = a_full + kStages;                          // [kStages]
+    uint64_t *t_full = a_empty + kStages;                          // [2]
+    uint64_t *t_empty = t_full + 2;                                // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 2);
+    unsigned char *sB = smem + kBarBytes;                          // 3 blocks of m_pad*32 bytes
+    const uint32_t b_block_bytes = P.m_pad * 32;
+    unsigned char *sA = sB + 3 * b_block_bytes;                    // kStages stages of 3 blocks
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t n_tiles = P.m_pad / NT;
+    const uint64_t n_rb = (P.n + kRows - 1) / kRows;
+
+    // ---- one-time setup: barriers, TMEM, node operands ----------------------------------------------------------
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; s++) { mbar_init(&a_full[s], 128); mbar_init(&a_empty[s], 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(&t_full[b], 1); mbar_init(&t_empty[b], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * NT)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (uint32_t p = threadIdx.x; p < P.m_pad; p += blockDim.x) {
+        float f[16];
+        const float4 *row = reinterpret_cast<const float4 *>(P.fnode_c + (size_t)p * 16);
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const float4 v = __ldg(row + q); f[4 * q] = v.x; f[4 * q + 1] = v.y; f[4 * q + 2] = v.z; f[4 * q + 3] = v.w; }
+        store_row_split(sB, b_block_bytes, P.m_pad * 16, p, f);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // ===== producers: object rows -> bf16 h/m/l operand blocks =====
+        const uint32_t r = threadIdx.x;   // 0..127
+        uint32_t it = 0;
+        for (uint64_t rb = blockIdx.x; rb < n_rb; rb += gridDim.x, it++) {
+            const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+            mbar_wait(&a_empty[s], ph ^ 1);
+            const uint64_t row = rb * kRows + r;
+            float f[16];
+            if (row < P.n) {
+                const float4 *src = reinterpret_cast<const float4 *>(P.fobj + row * 16);
+#pragma unroll
+                for (int q = 0; q < 4; q++) { const float4 v = __ldg(src + q); f[4 * q] = v.x; f[4 * q + 1] = v.y; f[4 * q + 2] = v.z; f[4 * q + 3] = v.w; }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 16; k++) f[k] = 0.f;
+            }
+            store_row_split(sA + s * kAStageBytes, kABlockBytes, kRows * 16, r, f);
+            fence_proxy_async();             // generic-proxy stores -> visible to the tensor core (async proxy)
+            mbar_arrive(&a_full[s]);
+        }
+    } else if (warp == 8) {
+        // ===== MMA issuer (one lane) =====
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
+            // (A term, B term) in increasing magnitude: hl, lh, mm, hm, mh, hh   (0 = h, 1 = m, 2 = l)
+            const int ta[6] = {0, 2, 1, 0, 1, 0}, tb[6] = {2, 0, 1, 1, 0, 0};
+            uint32_t it = 0, g = 0;
+            for (uint64_t rb = blockIdx.x; rb < n_rb; rb += gridDim.x, it++) {
+                const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                mbar_wait(&a_full[s], ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(sA + s * kAStageBytes);
+                for (uint32_t t = 0; t < n_tiles; t++, g++) {
+                    const uint32_t buf = g & 1, pht = (g >> 1) & 1;
+                    mbar_wait(&t_empty[buf], pht ^ 1);
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + buf * NT;
+#pragma unroll
+                    for (int q = 0; q < 6; q++) {
+                        const uint64_t da = make_desc(a_addr + ta[q] * kABlockBytes, P.lbo_a, P.sbo_a);
+                        const uint64_t db = make_desc(smem_u32(sB) + tb[q] * b_block_bytes + t * NT * 16, P.lbo_b, P.sbo_b);
+                        umma_bf16(d, da, db, idesc, q > 0 ? 1u : 0u);
+                    }
+                    umma_commit(&t_full[buf]);          // accumulator ready (implies fence::before_thread_sync)
+                }
+                umma_commit(&a_empty[s]);               // operand stage free once every MMA above has read it
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue warps 4..7: TMEM -> registers -> running (best value, best group of 8 columns) =====
+        const uint32_t q = warp & 3;                    // TMEM lane quarter this warp may access
+        const uint32_t lane_base = (q * 32) << 16;
+        uint32_t it = 0, g = 0;
+        for (uint64_t rb = blockIdx.x; rb < n_rb; rb += gridDim.x, it++) {
+            float best = -INFINITY;
+            uint32_t bgroup = 0;
+            for (uint32_t t = 0; t < n_tiles; t++, g++) {
+                const uint32_t buf = g & 1, pht = (g >> 1) & 1;
+                mbar_wait(&t_full[buf], pht);
+                tc_fence_after();
+#pragma unroll 1
+                for (uint32_t c = 0; c < NT / 32; c++) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + lane_base + buf * NT + c * 32, v);
+                    tmem_wait_ld();
+                    const uint32_t col0 = t * NT + c * 32;
+                    if (col0 + 32 > P.n_live) {          // warp-uniform: only the padded tail of the last tile
+#pragma unroll
+                        for (int i = 0; i < 32; i++) if (col0 + i >= P.n_live) v[i] = 0xFF800000u;   // -inf
+                    }
+#pragma unroll
+                    for (int gq = 0; gq < 4; gq++) {
+                        const float *f = reinterpret_cast<const float *>(&v[gq * 8]);
+                        const float gm = fmaxf(max3f(max3f(f[0], f[1], f[2]), f[3], f[4]), max3f(f[5], f[6], f[7]));
+                        if (gm > best) { best = gm; bgroup = (col0 >> 3) + gq; }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&t_empty[buf]);
+            }
+            // resolve: the 8 candidates of the winning group, re-evaluated in fp32 with the CUDA-core kernel's fmaf order
+            const uint64_t row = rb * kRows + q * 32 + lane;
+            if (row < P.n) {
+                float fo[16];
+                const float4 *src = reinterpret_cast<const float4 *>(P.fobj + row * 16);
+#pragma unroll
+                for (int w = 0; w < 4; w++) { const float4 x = __ldg(src + w); fo[4 * w] = x.x; fo[4 * w + 1] = x.y; fo[4 * w + 2] = x.z; fo[4 * w + 3] = x.w; }
+                float bc = 0.f; uint32_t bp = kNone;
+                for (uint32_t cnd = 0; cnd < 8; cnd++) {
+                    const uint32_t p = bgroup * 8 + cnd;
+                    if (p >= P.n_live) break;
+                    const float4 *nr = reinterpret_cast<const float4 *>(P.fnode_c + (size_t)p * 16);
+                    float acc = 0.f;
+#pragma unroll
+                    for (int w = 0; w < 4; w++) {
+                        const float4 x = __ldg(nr + w);
+                        acc = fmaf(fo[4 * w + 0], x.x, acc); acc = fmaf(fo[4 * w + 1], x.y, acc);
+                        acc = fmaf(fo[4 * w + 2], x.z, acc); acc = fmaf(fo[4 * w + 3], x.w, acc);
+                    }
+                    const float cst = -acc;
+                    if (bp == kNone || cst < bc) { bc = cst; bp = p; }
+                }
+                const uint32_t nid = bp == kNone ? kNone : __ldg(P.nidx_map + bp);
+                P.out_idx[row] = nid;
+                if (P.out_cost) P.out_cost[row] = bc;
+                if (P.counters && nid != kNone) atomicAdd(&P.counters[nid], 1u);
+            }
+        }
+    }
+
+    // ---- teardown -------------------------------------------------------------------------------------------
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * NT)) : "memory");
+    }
+}
+
+}  // namespace
+
+#define RIO_COUNT_LAUNCH(L) do { if ((L).launch_counter) ++*(L).launch_counter; } while (0)
+
+// Largest padded live-node count whose operands fit in shared memory beside the A stages.
+uint32_t affinity_umma_max_nodes() { return ((227u * 1024u - kBarBytes - kStages * kAStageBytes) / 96u) / 256u * 256u; }
+
+bool launch_assign_affinity_umma(const Launch &L, const float *d_fobj, uint64_t n, const float *d_fnode_c, const uint32_t *d_nidx_map, uint32_t n_live,
+                                 uint32_t m_pad, uint32_t *d_out_idx, float *d_out_cost, uint32_t *d_counters, bool swap_lbo_sbo) {
+    if (!n || !n_live) return false;
+    const bool small = m_pad <= 64;
+    if ((!small && (m_pad % 256)) || m_pad > affinity_umma_max_nodes()) return false;
+    UmmaParams P{d_fobj, n, d_fnode_c, d_nidx_map, n_live, m_pad, d_out_idx, d_out_cost, d_counters, kRows * 16u, 128u, m_pad * 16u, 128u};
+    if (swap_lbo_sbo) { P.lbo_a = 128u; P.sbo_a = kRows * 16u; P.lbo_b = 128u; P.sbo_b = m_pad * 16u; }
+    const size_t smem = kBarBytes + (size_t)3 * m_pad * 32 + (size_t)kStages * kAStageBytes;
+    const uint64_t n_rb = (n + kRows - 1) / kRows;
+    const int grid = (int)(n_rb < (uint64_t)L.sm_count ? n_rb : (uint64_t)L.sm_count);
+    if (small) {
+        cudaFuncSetAttribute(k_affinity_umma<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_affinity_umma<64><<<grid, kUmmaThreads, smem, L.stream>>>(P);
+    } else {
+        cudaFuncSetAttribute(k_affinity_umma<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_affinity_umma<256><<<grid, kUmmaThreads, smem, L.stream>>>(P);
+    }
+    RIO_COUNT_LAUNCH(L);
+    return true;
+}
+
+}  // namespace rio

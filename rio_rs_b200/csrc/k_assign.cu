@@ -2,7 +2,7 @@
 //
 // Weighted rendezvous: one thread owns OPT objects, the block walks the class-sorted
 // node table staged in shared memory (one broadcast LDS.128 per node per warp), and per (object,node) pair
-// the integer work is  p = s0*b + ab (IMAD);  t = p*C1 + s2 (IMAD.WIDE);  u = lo^hi (LOP3);  u > cur (ISETP).
+// the integer work is  p = s0*b + ab (IMAD);  q = p ^ (p>>15) ^ s1 (SHF, LOP3);  u = q*C1 + s2 (IMAD);  max (VIMNMX3 / 2).
 // The -log2 and the 64-bit weighted score are evaluated once per (object, weight class), not per pair.
 // The kernel is integer-ALU bound (12 B of HBM traffic per object against M pair hashes), see DESIGN.md 5.1.
 #include "kernels.cuh"
@@ -69,18 +69,16 @@ k_assign_hrw(const uint64_t *__restrict__ keys, uint64_t n_work, NodeTabDev tab,
                 const uint32_t seg_hi = min(c_end, chunk_hi);
                 if (q == c_start) {            // first node of the class seeds the running max
                     const uint4 r = srec[q - chunk_lo];
-                    const uint64_t s2 = ((uint64_t)r.w << 32) | r.z;
 #pragma unroll
-                    for (int k = 0; k < OPT; k++) { cu[k] = pair_hash(ObjHash{b[k], ab[k]}, r.x, s2); cj[k] = q; }
+                    for (int k = 0; k < OPT; k++) { cu[k] = pair_hash(ObjHash{b[k], ab[k]}, r.x, r.z, r.w); cj[k] = q; }
                     q++;
                 }
 #pragma unroll 4
                 for (; q < seg_hi; q++) {
                     const uint4 r = srec[q - chunk_lo];
-                    const uint64_t s2 = ((uint64_t)r.w << 32) | r.z;
 #pragma unroll
                     for (int k = 0; k < OPT; k++) {
-                        const uint32_t u = pair_hash(ObjHash{b[k], ab[k]}, r.x, s2);
+                        const uint32_t u = pair_hash(ObjHash{b[k], ab[k]}, r.x, r.z, r.w);
                         if (u > cu[k]) { cu[k] = u; cj[k] = q; }
                     }
                 }
@@ -116,7 +114,7 @@ k_assign_hrw(const uint64_t *__restrict__ keys, uint64_t n_work, NodeTabDev tab,
 
 
 // ---- v2: grouped 3-input max, index resolved afterwards -------------------------------------------------
-// Per pair only the hash (IMAD, IMAD.WIDE, LOP3) and half a VIMNMX3 are issued: the running maximum of a
+// Per pair only the hash (IMAD, SHF, LOP3, IMAD) and half a VIMNMX3 are issued: the running maximum of a
 // group of <= 32 consecutive nodes of one weight class is folded with __vimax3_u32, the group that raised the
 // class maximum is remembered by its start position, and the node index is recovered at the very end by
 // re-hashing the single winning group (<= 32 pairs per object, ~3 % extra at M = 1024).
@@ -127,13 +125,13 @@ __device__ __forceinline__ uint32_t resolve_in_group(ObjHash o, const NodeTabDev
     const uint4 *grec = reinterpret_cast<const uint4 *>(tab.recs);
     for (uint32_t q = gs; q < ge; q++) {
         const uint4 r = __ldg(grec + q);
-        if (pair_hash(o, r.x, ((uint64_t)r.w << 32) | r.z) == u_target) return r.y;
+        if (pair_hash(o, r.x, r.z, r.w) == u_target) return r.y;
     }
     return kNone;  // unreachable: the group produced u_target
 }
 
-template <int OPT>
-__global__ void __launch_bounds__(kAssignThreads, 2)
+template <int OPT, int MINB>
+__global__ void __launch_bounds__(kAssignThreads, MINB)
 k_assign_hrw_v2(const uint64_t *__restrict__ keys, uint64_t n_work, NodeTabDev tab, uint32_t *__restrict__ out_idx,
                 uint32_t *__restrict__ counters, const uint32_t *__restrict__ sel, uint32_t chunk_cap, uint32_t hist_bins) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -195,16 +193,14 @@ k_assign_hrw_v2(const uint64_t *__restrict__ keys, uint64_t n_work, NodeTabDev t
 #pragma unroll 4
                     for (; p + 1 < ge; p += 2) {
                         const uint4 r0 = srec[p - chunk_lo], r1 = srec[p + 1 - chunk_lo];
-                        const uint64_t s20 = ((uint64_t)r0.w << 32) | r0.z, s21 = ((uint64_t)r1.w << 32) | r1.z;
 #pragma unroll
                         for (int k = 0; k < OPT; k++)
-                            gm[k] = __vimax3_u32(gm[k], pair_hash(ObjHash{b[k], ab[k]}, r0.x, s20), pair_hash(ObjHash{b[k], ab[k]}, r1.x, s21));
+                            gm[k] = __vimax3_u32(gm[k], pair_hash(ObjHash{b[k], ab[k]}, r0.x, r0.z, r0.w), pair_hash(ObjHash{b[k], ab[k]}, r1.x, r1.z, r1.w));
                     }
                     if (p < ge) {
                         const uint4 r0 = srec[p - chunk_lo];
-                        const uint64_t s20 = ((uint64_t)r0.w << 32) | r0.z;
 #pragma unroll
-                        for (int k = 0; k < OPT; k++) gm[k] = max(gm[k], pair_hash(ObjHash{b[k], ab[k]}, r0.x, s20));
+                        for (int k = 0; k < OPT; k++) gm[k] = max(gm[k], pair_hash(ObjHash{b[k], ab[k]}, r0.x, r0.z, r0.w));
                     }
 #pragma unroll
                     for (int k = 0; k < OPT; k++)
@@ -347,7 +343,7 @@ k_assign_affinity_generic(const float *__restrict__ fobj, uint64_t n, const floa
 }
 
 
-// Register-only replay of the assign inner loop (same IMAD / IMAD.WIDE / LOP3 / VIMNMX3 mix, no shared or global
+// Register-only replay of the assign inner loop (same IMAD / SHF / LOP3 / IMAD / VIMNMX3 mix, no shared or global
 // memory in the loop): its pair rate is the integer-ALU roofline the assign kernel is reported against.
 __global__ void __launch_bounds__(kAssignThreads, 2)
 k_mix_rate(uint32_t iters, uint32_t *sink) {
@@ -357,13 +353,13 @@ k_mix_rate(uint32_t iters, uint32_t *sink) {
         b[k] = sink[8 + ((threadIdx.x * 8 + k) & 255)] | 1u; ab[k] = sink[8 + ((threadIdx.x * 8 + 4 + k) & 255)]; gm[k] = 0;
     }
     uint32_t s0a = blockIdx.x * 0x9E3779B9u + 12345u, s0b = s0a ^ 0x7F4A7C15u;
-    uint64_t s2a = 0xA0761D6478BD642Full ^ s0a, s2b = 0xE7037ED1A0B428DBull ^ s0b;
+    const uint32_t s1a = 0x6478BD64u ^ s0a, s1b = 0xA0B428DBu ^ s0b, s2a = 0xA0761D64u + s0a, s2b = 0xE7037ED1u + s0b;
     for (uint32_t it = 0; it < iters; it++) {
 #pragma unroll
         for (int r = 0; r < 8; r++) {
 #pragma unroll
             for (int k = 0; k < 4; k++)
-                gm[k] = __vimax3_u32(gm[k], pair_hash(ObjHash{b[k], ab[k]}, s0a, s2a), pair_hash(ObjHash{b[k], ab[k]}, s0b, s2b));
+                gm[k] = __vimax3_u32(gm[k], pair_hash(ObjHash{b[k], ab[k]}, s0a, s1a, s2a), pair_hash(ObjHash{b[k], ab[k]}, s0b, s1b, s2b));
             s0a = s0a * 747796405u + 2891336453u; s0b = s0b * 1664525u + 1013904223u;   // next two "nodes": 2 IMAD per 8 pairs (the real loop has 2 LDS.128 there)
         }
     }
@@ -458,16 +454,37 @@ void launch_assign_hrw(const Launch &L, const uint64_t *d_keys, uint64_t n, cons
     const uint32_t chunk_cap = tab.n_live < 1 ? 1 : (tab.n_live < 8192 ? tab.n_live : 8192);
     const uint32_t hist_bins = (d_counters && tab.n_total <= 8192) ? tab.n_total : 0;
     const size_t smem = (size_t)chunk_cap * sizeof(uint4) + (size_t)hist_bins * 4;
-    cudaFuncSetAttribute(k_assign_hrw<kOPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16 + 8192 * 4);
-    cudaFuncSetAttribute(k_assign_hrw_v2<kOPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16 + 8192 * 4);
-    const uint64_t tiles = (n_work + (uint64_t)kAssignThreads * kOPT - 1) / ((uint64_t)kAssignThreads * kOPT);
-    int bps = smem > 100 * 1024 ? 1 : (smem > 48 * 1024 ? 2 : 4);
-    uint64_t cap = (uint64_t)L.sm_count * bps;
-    int grid = (int)(tiles < cap ? tiles : cap);
-    if (assign_variant() == 1)
-        k_assign_hrw<kOPT><<<grid, kAssignThreads, smem, L.stream>>>(d_keys, n_work, tab, d_out_idx, d_counters, d_sel, chunk_cap, hist_bins);
-    else
-        k_assign_hrw_v2<kOPT><<<grid, kAssignThreads, smem, L.stream>>>(d_keys, n_work, tab, d_out_idx, d_counters, d_sel, chunk_cap, hist_bins);
+    if (assign_variant() == 1) {
+        cudaFuncSetAttribute(k_assign_hrw<kOPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16 + 8192 * 4);
+        const uint64_t tiles = (n_work + (uint64_t)kAssignThreads * kOPT - 1) / ((uint64_t)kAssignThreads * kOPT);
+        const int bps = smem > 100 * 1024 ? 1 : 2;
+        const uint64_t cap = (uint64_t)L.sm_count * bps;
+        k_assign_hrw<kOPT><<<(int)(tiles < cap ? tiles : cap), kAssignThreads, smem, L.stream>>>(d_keys, n_work, tab, d_out_idx, d_counters, d_sel, chunk_cap, hist_bins);
+    } else {
+        // RIO_ASSIGN_TUNE="<objects per thread><min CTAs per SM>" selects a compiled tuning point (A/B runs); default 42
+        const char *t = getenv("RIO_ASSIGN_TUNE");
+        const int tune = (t && t[0] && t[1]) ? (t[0] - '0') * 10 + (t[1] - '0') : 42;
+#define RIO_LAUNCH_V2(OPT_, MINB_)                                                                                                    \
+        do {                                                                                                                          \
+            cudaFuncSetAttribute(k_assign_hrw_v2<OPT_, MINB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16 + 8192 * 4);     \
+            const uint64_t tiles = (n_work + (uint64_t)kAssignThreads * OPT_ - 1) / ((uint64_t)kAssignThreads * OPT_);                \
+            int bps = MINB_;                                                                                                          \
+            while (bps > 1 && (size_t)bps * (smem + 1024) > 227u * 1024u) bps--;                                                      \
+            const uint64_t cap = (uint64_t)L.sm_count * bps;                                                                          \
+            k_assign_hrw_v2<OPT_, MINB_><<<(int)(tiles < cap ? tiles : cap), kAssignThreads, smem, L.stream>>>(d_keys, n_work, tab, d_out_idx, d_counters, \
+                                                                                                            d_sel, chunk_cap, hist_bins); \
+        } while (0)
+        switch (tune) {
+            case 22: RIO_LAUNCH_V2(2, 2); break;
+            case 23: RIO_LAUNCH_V2(2, 3); break;
+            case 24: RIO_LAUNCH_V2(2, 4); break;
+            case 43: RIO_LAUNCH_V2(4, 3); break;
+            case 81: RIO_LAUNCH_V2(8, 1); break;
+            case 82: RIO_LAUNCH_V2(8, 2); break;
+            default: RIO_LAUNCH_V2(4, 2); break;
+        }
+#undef RIO_LAUNCH_V2
+    }
     RIO_COUNT_LAUNCH(L);
 }
 

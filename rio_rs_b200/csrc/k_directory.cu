@@ -177,11 +177,11 @@ k_dir_count(DirDev dir, unsigned long long *placed, uint32_t *counters, uint32_t
 // the stream is 12 B/object for a dense set, 16 B/slot for the directory).  by_idx[] gives {s0, invw, s2}.
 __device__ __forceinline__ bool join_wins(uint64_t key, uint32_t cur, uint32_t new_idx, const uint4 nn, const uint4 *__restrict__ by_idx) {
     const ObjHash o = obj_hash(key);
-    const uint32_t un = pair_hash(o, nn.x, ((uint64_t)nn.w << 32) | nn.z);
+    const uint32_t un = pair_hash(o, nn.x, nn.z, nn.w);
     const uint64_t sn = (uint64_t)elog(un) * nn.y;
     const uint4 c = __ldg(by_idx + cur);
     if (c.y == 0) return true;   // incumbent is not live any more
-    const uint32_t uc = pair_hash(o, c.x, ((uint64_t)c.w << 32) | c.z);
+    const uint32_t uc = pair_hash(o, c.x, c.z, c.w);
     const uint64_t sc = (uint64_t)elog(uc) * c.y;
     return cand_better(sn, un, new_idx, sc, uc, cur);
 }
@@ -251,7 +251,7 @@ __device__ uint32_t hrw_scalar(uint64_t key, const NodeTabDev &tab) {
         uint32_t cu = 0, ci = kNone;
         for (uint32_t q = r0.start; q < r1.start; q++) {
             const uint4 r = __ldg(grec + q);
-            const uint32_t u = pair_hash(o, r.x, ((uint64_t)r.w << 32) | r.z);
+            const uint32_t u = pair_hash(o, r.x, r.z, r.w);
             if (ci == kNone || u > cu) { cu = u; ci = r.y; }
         }
         const uint64_t sc = (uint64_t)elog(cu) * r0.invw;

@@ -11,8 +11,8 @@ namespace rio {
 struct __align__(16) NodeRec {
     uint32_t s0;    // lo32(seed)
     uint32_t nidx;  // interned node index (what the directory stores)
-    uint32_t s2lo;  // mix64(seed ^ kSaltNode2)
-    uint32_t s2hi;
+    uint32_t s1;    // hi32(seed)
+    uint32_t s2;    // lo32(mix64(seed ^ kSaltNode2))
 };
 struct ClassRec {
     uint32_t start;  // first record of the class in the sorted table
@@ -25,7 +25,7 @@ struct NodeTabDev {
     uint32_t n_classes;
     uint32_t n_total;          // interned nodes (size of counter / by-index arrays)
     // by-interned-index arrays (n_total entries) for the kernels that gather by node index
-    const uint4 *by_idx;       // {s0, invw (0 = not live), s2lo, s2hi}
+    const uint4 *by_idx;       // {s0, invw (0 = not live), s1, s2}
 };
 
 // ---- directory: open addressing, 16-byte AoS slots ------------------------------------------------------
@@ -50,6 +50,10 @@ void launch_assign_hrw(const Launch &L, const uint64_t *d_keys, uint64_t n, cons
 void launch_assign_affinity(const Launch &L, const float *d_fobj, uint64_t n, const float *d_fnode /*n_total x K*/,
                             const uint32_t *d_live /*n_total flags*/, uint32_t n_total, uint32_t K, uint32_t *d_out_idx,
                             float *d_out_cost /*nullable*/, uint32_t *d_counters);
+// tcgen05/TMEM path for K == 16 (k_affinity_umma.cu); returns false when the shape is not supported (caller falls back to FFMA kernel)
+uint32_t affinity_umma_max_nodes();
+bool launch_assign_affinity_umma(const Launch &L, const float *d_fobj, uint64_t n, const float *d_fnode_c, const uint32_t *d_nidx_map, uint32_t n_live,
+                                 uint32_t m_pad, uint32_t *d_out_idx, float *d_out_cost, uint32_t *d_counters, bool swap_lbo_sbo);
 uint64_t launch_mix_rate(const Launch &L, uint32_t iters, uint32_t *d_sink);
 void launch_synth_keys(const Launch &L, uint64_t *d_keys, uint64_t first, uint64_t n, uint64_t seed);
 void launch_hash_ids(const Launch &L, const char *d_packed, const uint64_t *d_offsets, uint64_t n, uint64_t *d_keys);

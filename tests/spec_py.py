@@ -54,11 +54,11 @@ def pair_hash(key, seed):
     a = h & M32
     b = (h >> 32) | 1
     ab = a * b & M32
-    s0 = seed & M32
-    s2 = mix64(seed ^ 0xA0761D6478BD642F)
+    s0, s1 = seed & M32, seed >> 32
+    s2 = mix64(seed ^ 0xA0761D6478BD642F) & M32
     p = (s0 * b + ab) & M32
-    t = (p * 0x9E3779B1 + s2) & M64
-    return (t & M32) ^ (t >> 32)
+    q = p ^ (p >> 15) ^ s1
+    return (q * 0x9E3779B1 + s2) & M32
 
 
 def inv_weight(w):
