@@ -20,6 +20,7 @@
 #include "spec.cuh"
 
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 namespace rio {
 
@@ -118,10 +119,10 @@ struct UmmaParams {
     uint32_t *out_idx;
     float *out_cost;          // nullable
     uint32_t *counters;       // nullable
-    uint32_t lbo_a, sbo_a, lbo_b, sbo_b;   // descriptor strides in bytes (passed from the host so a probe run can flip them)
+    uint32_t lbo_a, sbo_a, lbo_b, sbo_b;   // descriptor strides in bytes
 };
 
-template <int NT>
+template <int NT, int LDW>
 __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *a_full = reinterpret_cast<uint64_t *>(smem);         // [kStages]
@@ -223,20 +224,24 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
                 mbar_wait(&t_full[buf], pht);
                 tc_fence_after();
 #pragma unroll 1
-                for (uint32_t c = 0; c < NT / 32; c++) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + lane_base + buf * NT + c * 32, v);
+                for (uint32_t c0 = 0; c0 < NT / 32; c0 += LDW) {
+                    uint32_t v[LDW][32];
+#pragma unroll
+                    for (int w = 0; w < LDW; w++) tmem_ld32(tmem_base + lane_base + buf * NT + (c0 + w) * 32, v[w]);   // LDW loads in flight
                     tmem_wait_ld();
-                    const uint32_t col0 = t * NT + c * 32;
-                    if (col0 + 32 > P.n_live) {          // warp-uniform: only the padded tail of the last tile
 #pragma unroll
-                        for (int i = 0; i < 32; i++) if (col0 + i >= P.n_live) v[i] = 0xFF800000u;   // -inf
-                    }
+                    for (int w = 0; w < LDW; w++) {
+                        const uint32_t col0 = t * NT + (c0 + w) * 32;
+                        if (col0 + 32 > P.n_live) {          // warp-uniform: only the padded tail of the last tile
 #pragma unroll
-                    for (int gq = 0; gq < 4; gq++) {
-                        const float *f = reinterpret_cast<const float *>(&v[gq * 8]);
-                        const float gm = fmaxf(max3f(max3f(f[0], f[1], f[2]), f[3], f[4]), max3f(f[5], f[6], f[7]));
-                        if (gm > best) { best = gm; bgroup = (col0 >> 3) + gq; }
+                            for (int i = 0; i < 32; i++) if (col0 + i >= P.n_live) v[w][i] = 0xFF800000u;   // -inf
+                        }
+#pragma unroll
+                        for (int gq = 0; gq < 4; gq++) {
+                            const float *f = reinterpret_cast<const float *>(&v[w][gq * 8]);
+                            const float gm = fmaxf(max3f(max3f(f[0], f[1], f[2]), f[3], f[4]), max3f(f[5], f[6], f[7]));
+                            if (gm > best) { best = gm; bgroup = (col0 >> 3) + gq; }
+                        }
                     }
                 }
                 tc_fence_before();
@@ -289,21 +294,30 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
 uint32_t affinity_umma_max_nodes() { return ((227u * 1024u - kBarBytes - kStages * kAStageBytes) / 96u) / 256u * 256u; }
 
 bool launch_assign_affinity_umma(const Launch &L, const float *d_fobj, uint64_t n, const float *d_fnode_c, const uint32_t *d_nidx_map, uint32_t n_live,
-                                 uint32_t m_pad, uint32_t *d_out_idx, float *d_out_cost, uint32_t *d_counters, bool swap_lbo_sbo) {
+                                 uint32_t m_pad, uint32_t *d_out_idx, float *d_out_cost, uint32_t *d_counters) {
     if (!n || !n_live) return false;
     const bool small = m_pad <= 64;
     if ((!small && (m_pad % 256)) || m_pad > affinity_umma_max_nodes()) return false;
+    // K-major interleaved operands: LBO = distance between the two 16-byte K chunks, SBO = distance between 8-row groups
+    // (confirmed on hardware: profiles/r01_umma_first_light.txt)
     UmmaParams P{d_fobj, n, d_fnode_c, d_nidx_map, n_live, m_pad, d_out_idx, d_out_cost, d_counters, kRows * 16u, 128u, m_pad * 16u, 128u};
-    if (swap_lbo_sbo) { P.lbo_a = 128u; P.sbo_a = kRows * 16u; P.lbo_b = 128u; P.sbo_b = m_pad * 16u; }
     const size_t smem = kBarBytes + (size_t)3 * m_pad * 32 + (size_t)kStages * kAStageBytes;
     const uint64_t n_rb = (n + kRows - 1) / kRows;
     const int grid = (int)(n_rb < (uint64_t)L.sm_count ? n_rb : (uint64_t)L.sm_count);
+    const char *e = getenv("RIO_UMMA_LDW");   // TMEM loads in flight per wait (A/B runs): 1, 2 (default) or 4
+    const int ldw = e ? atoi(e) : 2;
     if (small) {
-        cudaFuncSetAttribute(k_affinity_umma<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_affinity_umma<64><<<grid, kUmmaThreads, smem, L.stream>>>(P);
+        cudaFuncSetAttribute(k_affinity_umma<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_affinity_umma<64, 2><<<grid, kUmmaThreads, smem, L.stream>>>(P);
+    } else if (ldw == 1) {
+        cudaFuncSetAttribute(k_affinity_umma<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_affinity_umma<256, 1><<<grid, kUmmaThreads, smem, L.stream>>>(P);
+    } else if (ldw == 4) {
+        cudaFuncSetAttribute(k_affinity_umma<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_affinity_umma<256, 4><<<grid, kUmmaThreads, smem, L.stream>>>(P);
     } else {
-        cudaFuncSetAttribute(k_affinity_umma<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_affinity_umma<256><<<grid, kUmmaThreads, smem, L.stream>>>(P);
+        cudaFuncSetAttribute(k_affinity_umma<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_affinity_umma<256, 2><<<grid, kUmmaThreads, smem, L.stream>>>(P);
     }
     RIO_COUNT_LAUNCH(L);
     return true;

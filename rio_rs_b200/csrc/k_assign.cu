@@ -461,9 +461,9 @@ void launch_assign_hrw(const Launch &L, const uint64_t *d_keys, uint64_t n, cons
         const uint64_t cap = (uint64_t)L.sm_count * bps;
         k_assign_hrw<kOPT><<<(int)(tiles < cap ? tiles : cap), kAssignThreads, smem, L.stream>>>(d_keys, n_work, tab, d_out_idx, d_counters, d_sel, chunk_cap, hist_bins);
     } else {
-        // RIO_ASSIGN_TUNE="<objects per thread><min CTAs per SM>" selects a compiled tuning point (A/B runs); default 42
+        // RIO_ASSIGN_TUNE="<objects per thread><min CTAs per SM>" selects a compiled tuning point (A/B runs); default 43 (profiles/r01_tune_assign.txt)
         const char *t = getenv("RIO_ASSIGN_TUNE");
-        const int tune = (t && t[0] && t[1]) ? (t[0] - '0') * 10 + (t[1] - '0') : 42;
+        const int tune = (t && t[0] && t[1]) ? (t[0] - '0') * 10 + (t[1] - '0') : 43;
 #define RIO_LAUNCH_V2(OPT_, MINB_)                                                                                                    \
         do {                                                                                                                          \
             cudaFuncSetAttribute(k_assign_hrw_v2<OPT_, MINB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16 + 8192 * 4);     \
@@ -478,10 +478,10 @@ void launch_assign_hrw(const Launch &L, const uint64_t *d_keys, uint64_t n, cons
             case 22: RIO_LAUNCH_V2(2, 2); break;
             case 23: RIO_LAUNCH_V2(2, 3); break;
             case 24: RIO_LAUNCH_V2(2, 4); break;
-            case 43: RIO_LAUNCH_V2(4, 3); break;
+            case 42: RIO_LAUNCH_V2(4, 2); break;
             case 81: RIO_LAUNCH_V2(8, 1); break;
             case 82: RIO_LAUNCH_V2(8, 2); break;
-            default: RIO_LAUNCH_V2(4, 2); break;
+            default: RIO_LAUNCH_V2(4, 3); break;
         }
 #undef RIO_LAUNCH_V2
     }

@@ -242,8 +242,11 @@ def test_golden_vectors_on_gpu(gp):
 
 
 # ---- solver: affinity cost, 1e-5 relative ------------------------------------------------------------------------
-@pytest.mark.parametrize("K,M,n", [(16, 1024, 60000), (16, 37, 5001), (8, 64, 3000), (5, 9, 1000)])
-def test_affinity_cost_argmin(gp, oracle, K, M, n):
+@pytest.mark.parametrize("variant", ["umma", "ffma"])
+@pytest.mark.parametrize("K,M,n", [(16, 1024, 60000), (16, 37, 5001), (16, 64, 999), (16, 65, 7000), (16, 300, 20000), (16, 2000, 4000), (8, 64, 3000), (5, 9, 1000)])
+def test_affinity_cost_argmin(gp, oracle, K, M, n, variant):
+    """cost = -dot, argmin.  K == 16 runs on the tensor cores (tcgen05, bf16x3 split) unless
+    RIO_AFFINITY_VARIANT=ffma or the node set does not fit shared memory (M = 2000); other K use CUDA cores."""
     rng = np.random.default_rng(11)
     fo = rng.uniform(-1, 1, (n, K)).astype(np.float32)
     fn = np.random.default_rng(13).uniform(-1, 1, (M, K)).astype(np.float32)
@@ -251,9 +254,19 @@ def test_affinity_cost_argmin(gp, oracle, K, M, n):
     w = np.ones(M, dtype=np.uint32)
     if M > 4:
         w[3] = 0
-    p = provider(gp)
-    p.set_nodes(addrs, w, fn)
-    got = p.assign_batch(obj_feats=fo)
+        w[M - 1] = 0
+    os.environ["RIO_AFFINITY_VARIANT"] = variant
+    try:
+        p = provider(gp)
+        p.set_nodes(addrs, w, fn)
+        got = p.assign_batch(obj_feats=fo)
+        s = p.new_set(n)
+        s.load_keys(np.arange(n, dtype=np.uint64))
+        s.load_feats(fo)
+        s.assign(True)
+        assert (s.read() == got).all() and (s.counters() == np.bincount(got, minlength=M)).all()
+    finally:
+        os.environ.pop("RIO_AFFINITY_VARIANT", None)
     idx, cost, gap = oracle.assign_affinity(fo, fn, w, threads=8)
     # index must match unless the fp64 top-2 gap is below the tolerance (then either node is accepted);
     # in every case the fp64 cost of the chosen node is within 1e-5 relative of the optimum
@@ -263,6 +276,30 @@ def test_affinity_cost_argmin(gp, oracle, K, M, n):
     chosen = -(fo.astype(np.float64) * fn.astype(np.float64)[got]).sum(1)
     assert (np.abs(chosen - cost) <= tol).all()
     assert (w[got] > 0).all()
+
+
+def test_affinity_bf16_exact_inputs_are_bit_stable(gp, oracle):
+    """bf16-representable features (SURVEY 8d variant): every cross term is exact, so the tensor-core path and the
+    CUDA-core path must pick identical nodes."""
+    rng = np.random.default_rng(3)
+    def bf16_round(x):
+        u = x.astype(np.float32).view(np.uint32)
+        return ((u + 0x8000) & 0xFFFF0000).astype(np.uint32).view(np.float32)
+    fo = bf16_round(rng.uniform(-1, 1, (30000, 16)))
+    fn = bf16_round(rng.uniform(-1, 1, (512, 16)))
+    addrs, _, _ = oracle.synth_nodes(512)
+    p = provider(gp)
+    p.set_nodes(addrs, None, fn)
+    res = {}
+    for v in ("umma", "ffma"):
+        os.environ["RIO_AFFINITY_VARIANT"] = v
+        try:
+            res[v] = p.assign_batch(obj_feats=fo)
+        finally:
+            os.environ.pop("RIO_AFFINITY_VARIANT", None)
+    idx, cost, gap = oracle.assign_affinity(fo, fn, np.ones(512, dtype=np.uint32), threads=8)
+    assert (res["umma"] == res["ffma"]).all()
+    assert ((res["umma"] == idx) | (gap <= 1e-5 * np.abs(cost))).all()
 
 
 # ---- resident sets: bounded-load rounds, rebalance storm ----------------------------------------------------------

@@ -9,8 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import rio_rs_b200 as R
 from oracle import pyoracle as O
 
-swap = sys.argv[1] if len(sys.argv) > 1 else "0"
-os.environ["RIO_UMMA_SWAP"] = swap
+swap = "0"
 for (M, n) in [(1024, 100_000), (37, 5001), (300, 20_000)]:
     rng = np.random.default_rng(11)
     fo = rng.uniform(-1, 1, (n, 16)).astype(np.float32)
@@ -37,13 +36,14 @@ for (M, n) in [(1024, 100_000), (37, 5001), (300, 20_000)]:
         s.synth_keys(0, N, 1)
         big = np.random.default_rng(5).uniform(-1, 1, (N, 16)).astype(np.float32)
         s.load_feats(big)
-        for var in ("umma", "ffma"):
+        for var, ldw in (("umma", "1"), ("umma", "2"), ("umma", "4"), ("ffma", "2")):
             os.environ["RIO_AFFINITY_VARIANT"] = var
+            os.environ["RIO_UMMA_LDW"] = ldw
             s.assign(True); p.sync()
             p.event_record(0)
             for _ in range(3):
                 s.assign(True)
             p.event_record(1); p.sync()
             ms = p.event_elapsed_ms(0, 1) / 3
-            print("  10M x 1024 x K16 %s: %.3f ms  %.2f Gplacements/s  %.1f TFLOP/s(algorithmic 2KM)" % (var, ms, N / ms / 1e6, 2 * 16 * 1024 * N / ms / 1e9), flush=True)
+            print("  10M x 1024 x K16 %s ldw=%s: %.3f ms  %.2f Gplacements/s  %.1f TFLOP/s(algorithmic 2KM)" % (var, ldw, ms, N / ms / 1e6, 2 * 16 * 1024 * N / ms / 1e9), flush=True)
         del s
