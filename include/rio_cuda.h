@@ -196,6 +196,20 @@ rio_status  rio_cuda_lookup_str(rio_placement *h, const char *type, size_t type_
 rio_status  rio_cuda_clean_server_str(rio_placement *h, const char *address, size_t address_len);
 rio_status  rio_cuda_remove_str(rio_placement *h, const char *type, size_t type_len, const char *id, size_t id_len);
 
+/* ---- micro-batching resolver: the per-request call site (service.rs:193-254), coalesced ------------------------- */
+/* Service runs get_or_create_placement once per request on one task per connection (server.rs:303).  Concurrent
+ * rio_cuda_resolver_resolve calls (any number of threads) are coalesced into one rio_cuda_place_batch as soon as
+ * max_batch requests are pending or the oldest has waited max_wait_us; every caller gets its own answer back. */
+typedef struct rio_resolver rio_resolver;
+rio_status  rio_cuda_resolver_create(rio_placement *h, uint32_t policy, uint32_t self_idx, uint32_t max_batch,
+                                     uint32_t max_wait_us, rio_resolver **out);
+void        rio_cuda_resolver_destroy(rio_resolver *r);
+rio_status  rio_cuda_resolver_resolve(rio_resolver *r, uint64_t key, uint32_t *out_idx);
+rio_status  rio_cuda_resolver_resolve_str(rio_resolver *r, const char *type, size_t type_len, const char *id, size_t id_len,
+                                          char *buf, size_t cap, size_t *out_len);
+rio_status  rio_cuda_resolver_stats(rio_resolver *r, uint64_t *calls, uint64_t *batches, uint64_t *largest_batch);
+const char *rio_cuda_resolver_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,7 @@ from .provider import (  # noqa: F401
     ObjectPlacementError,
     ObjectPlacementItem,
     ObjectSet,
+    Resolver,
     Unknown,
     Upstream,
 )

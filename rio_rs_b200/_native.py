@@ -87,6 +87,12 @@ SIGNATURES = {
     "rio_cuda_event_elapsed_ms": (C.c_int32, [H, C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]),
     "rio_cuda_bench_mix_rate": (C.c_int32, [H, C.c_uint32, C.POINTER(C.c_double)]),
     "rio_cuda_launch_count": (C.c_int32, [H, u64p]),
+    "rio_cuda_resolver_create": (C.c_int32, [H, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(H)]),
+    "rio_cuda_resolver_destroy": (None, [H]),
+    "rio_cuda_resolver_resolve": (C.c_int32, [H, C.c_uint64, u32p]),
+    "rio_cuda_resolver_resolve_str": (C.c_int32, [H, C.c_char_p, sz, C.c_char_p, sz, C.c_char_p, sz, C.POINTER(sz)]),
+    "rio_cuda_resolver_stats": (C.c_int32, [H, u64p, u64p, u64p]),
+    "rio_cuda_resolver_last_error": (C.c_char_p, []),
     "rio_cuda_update_str": (C.c_int32, [H, C.c_char_p, sz, C.c_char_p, sz, C.c_char_p, sz]),
     "rio_cuda_lookup_str": (C.c_int32, [H, C.c_char_p, sz, C.c_char_p, sz, C.c_char_p, sz, C.POINTER(sz)]),
     "rio_cuda_clean_server_str": (C.c_int32, [H, C.c_char_p, sz]),

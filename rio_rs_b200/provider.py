@@ -283,6 +283,54 @@ class GpuObjectPlacement:
         return ObjectSet(self, capacity)
 
 
+class Resolver:
+    """Micro-batching front end for per-request resolves (Service::get_or_create_placement, service.rs:193-254)."""
+
+    def __init__(self, provider, policy="hrw", self_address=None, max_batch=4096, max_wait_us=50):
+        self.p = provider
+        self.L = provider.L
+        pol = N.PLACE_SELF if policy == "self" else N.PLACE_HRW
+        self_idx = 0
+        if pol == N.PLACE_SELF:
+            self_idx = provider.node_index(self_address)
+            if self_idx is None:
+                raise Unknown("self_address is not a known node")
+        r = N.H()
+        provider._ck(self.L.rio_cuda_resolver_create(provider.h, pol, self_idx, max_batch, max_wait_us, C.byref(r)))
+        self.r = r
+
+    def close(self):
+        if getattr(self, "r", None):
+            self.L.rio_cuda_resolver_destroy(self.r)
+            self.r = None
+
+    __del__ = close
+
+    def resolve(self, key):
+        out = C.c_uint32(0)
+        st = self.L.rio_cuda_resolver_resolve(self.r, int(key), C.byref(out))
+        if st != N.RIO_OK:
+            msg = self.L.rio_cuda_resolver_last_error()
+            raise (Upstream if st == N.RIO_ERR_UPSTREAM else Unknown)(msg.decode(errors="replace") if msg else "")
+        return out.value
+
+    def get_or_create_placement(self, handler_type, handler_id):
+        """Same signature as the reference's per-request function (service.rs:193-197): -> address string."""
+        t, i = handler_type.encode(), handler_id.encode()
+        buf = C.create_string_buffer(256)
+        n = C.c_size_t(0)
+        st = self.L.rio_cuda_resolver_resolve_str(self.r, t, len(t), i, len(i), buf, 256, C.byref(n))
+        if st != N.RIO_OK:
+            msg = self.L.rio_cuda_resolver_last_error()
+            raise (Upstream if st == N.RIO_ERR_UPSTREAM else Unknown)(msg.decode(errors="replace") if msg else "")
+        return None if n.value == C.c_size_t(-1).value else buf.raw[: n.value].decode()
+
+    def stats(self):
+        a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        self.L.rio_cuda_resolver_stats(self.r, C.byref(a), C.byref(b), C.byref(c))
+        return {"calls": a.value, "batches": b.value, "largest_batch": c.value}
+
+
 def comm_unique_id():
     buf = np.zeros(N.COMM_ID_BYTES, dtype=np.uint8)
     L = N.lib()

@@ -449,3 +449,46 @@ def test_full_size_10m_x_1024_properties(gp, oracle):
     assert moved2 == moved and (s.read() == idx).all()
     # same result through the host-buffer API (H2D/D2H pipelined path)
     assert (p.assign_batch(keys[:3_000_000]) == idx[:3_000_000]).all()
+
+
+# ---- micro-batched per-request resolves ------------------------------------------------------------
+def test_resolver_coalesces_concurrent_per_id_calls(gp, oracle):
+    """16 threads call get_or_create_placement per id, as Service does per request (service.rs:193-254, one task per
+    connection server.rs:303); the resolver must coalesce them into few place_batch launches and give every caller the
+    answer the restated reference policy gives."""
+    import threading
+
+    p, m = provider(gp), oracle.DirectoryModel()
+    addrs = ["0.0.0.0:%d" % (5000 + j) for j in range(4)]
+    p.set_nodes(addrs)
+    for a in addrs:
+        ip, port = a.split(":")
+        m.member_push(ip, port, True)
+    ids = [("MockService", str(i)) for i in range(4000)]
+    r = gp.Resolver(p, policy="self", self_address=addrs[1], max_batch=512, max_wait_us=200)
+    got = [None] * len(ids)
+
+    def work(t):
+        for k in range(t, len(ids), 16):
+            got[k] = r.get_or_create_placement(*ids[k])
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(16)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    want = [m.get_or_create_placement(addrs[1], *i) for i in ids]
+    assert got == want
+    st = r.stats()
+    assert st["calls"] == len(ids) and st["batches"] < st["calls"] // 2 and st["largest_batch"] > 1, st
+    # second pass from another "server": every id is already placed -> same owner (-> Redirect upstream)
+    r2 = gp.Resolver(p, policy="self", self_address=addrs[2])
+    assert [r2.get_or_create_placement(*i) for i in ids[:50]] == want[:50]
+    # rendezvous policy through the same front end
+    p3 = provider(gp)
+    a3, seeds, w = oracle.synth_nodes(32)
+    p3.set_nodes(a3, w)
+    r3 = gp.Resolver(p3, policy="hrw")
+    keys = oracle.synth_keys(300, 2)
+    assert [r3.resolve(int(k)) for k in keys] == oracle.assign_hrw(keys, seeds, w).tolist()
+    r.close(); r2.close(); r3.close()
