@@ -304,20 +304,20 @@ bool launch_assign_affinity_umma(const Launch &L, const float *d_fobj, uint64_t 
     const size_t smem = kBarBytes + (size_t)3 * m_pad * 32 + (size_t)kStages * kAStageBytes;
     const uint64_t n_rb = (n + kRows - 1) / kRows;
     const int grid = (int)(n_rb < (uint64_t)L.sm_count ? n_rb : (uint64_t)L.sm_count);
-    const char *e = getenv("RIO_UMMA_LDW");   // TMEM loads in flight per wait (A/B runs): 1, 2 (default) or 4
-    const int ldw = e ? atoi(e) : 2;
+    const char *e = getenv("RIO_UMMA_LDW");   // TMEM loads in flight per wait (A/B runs): 1, 2 or 4 (default, profiles/r01_umma_ldw.txt)
+    const int ldw = e ? atoi(e) : 4;
     if (small) {
         cudaFuncSetAttribute(k_affinity_umma<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k_affinity_umma<64, 2><<<grid, kUmmaThreads, smem, L.stream>>>(P);
     } else if (ldw == 1) {
         cudaFuncSetAttribute(k_affinity_umma<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k_affinity_umma<256, 1><<<grid, kUmmaThreads, smem, L.stream>>>(P);
-    } else if (ldw == 4) {
-        cudaFuncSetAttribute(k_affinity_umma<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_affinity_umma<256, 4><<<grid, kUmmaThreads, smem, L.stream>>>(P);
-    } else {
+    } else if (ldw == 2) {
         cudaFuncSetAttribute(k_affinity_umma<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k_affinity_umma<256, 2><<<grid, kUmmaThreads, smem, L.stream>>>(P);
+    } else {
+        cudaFuncSetAttribute(k_affinity_umma<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_affinity_umma<256, 4><<<grid, kUmmaThreads, smem, L.stream>>>(P);
     }
     RIO_COUNT_LAUNCH(L);
     return true;

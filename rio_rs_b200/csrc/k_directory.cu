@@ -30,6 +30,13 @@ __device__ __forceinline__ void warp_add(unsigned long long *ctr, bool pred) {
     if (m && (threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) atomicAdd(ctr, (unsigned long long)__popc(m));
 }
 
+// End-of-kernel variant for high hit rates: each thread accumulates locally over its grid-stride loop, then one atomic per warp.
+__device__ __forceinline__ void warp_flush(unsigned long long *ctr, unsigned long long local) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xFFFFFFFFu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(ctr, local);
+}
+
 __global__ void k_dir_init(DirSlot *slots, uint64_t cap) {
     uint4 *p = reinterpret_cast<uint4 *>(slots);
     const uint4 e = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u);  // key = EMPTY, val = (0 << 32) | NONE
@@ -61,6 +68,7 @@ k_dir_lookup(DirDev dir, const uint64_t *__restrict__ keys, uint64_t n, uint32_t
 __global__ void __launch_bounds__(256)
 k_dir_upsert(DirDev dir, const uint64_t *__restrict__ keys, const uint32_t *__restrict__ idx, uint32_t const_idx, uint64_t n,
              uint64_t *__restrict__ slot_scratch, unsigned long long *new_keys, uint32_t *error) {
+    unsigned long long n_fresh = 0;
     for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t i = base + threadIdx.x;
         bool fresh = false;
@@ -86,8 +94,9 @@ k_dir_upsert(DirDev dir, const uint64_t *__restrict__ keys, const uint32_t *__re
                 atomicExch(error, 1u);   // table full: the host sizes the table so this cannot happen
             }
         }
-        warp_add(new_keys, fresh);   // whole warp reaches this point (base loop is block-uniform)
+        n_fresh += fresh;
     }
+    warp_flush(new_keys, n_fresh);   // whole warp reaches this point (the base loop is block-uniform)
 }
 __global__ void __launch_bounds__(256)
 k_dir_upsert_finish(DirDev dir, const uint64_t *__restrict__ slot_scratch, uint64_t n) {
@@ -135,6 +144,7 @@ __global__ void __launch_bounds__(256)
 k_dir_rehash(DirDev from, DirDev to, unsigned long long *new_keys, uint32_t *error) {
     const uint4 *src = reinterpret_cast<const uint4 *>(from.slots);
     const uint64_t cap = from.mask + 1;
+    unsigned long long n_moved = 0;
     for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < cap; base += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t i = base + threadIdx.x;
         bool moved = false;
@@ -151,24 +161,26 @@ k_dir_rehash(DirDev from, DirDev to, unsigned long long *new_keys, uint32_t *err
                 if (!moved) atomicExch(error, 1u);
             }
         }
-        warp_add(new_keys, moved);
+        n_moved += moved;
     }
+    warp_flush(new_keys, n_moved);
 }
 
 __global__ void __launch_bounds__(256)
 k_dir_count(DirDev dir, unsigned long long *placed, uint32_t *counters, uint32_t n_total) {
     const uint4 *slots = reinterpret_cast<const uint4 *>(dir.slots);
     const uint64_t cap = dir.mask + 1;
+    unsigned long long n_hit = 0;
     for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < cap; base += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t i = base + threadIdx.x;
-        bool hit = false;
         if (i < cap) {
             const uint4 v = slots[i];
-            hit = (v.x & v.y) != 0xFFFFFFFFu && v.z != kNone;
+            const bool hit = (v.x & v.y) != 0xFFFFFFFFu && v.z != kNone;
             if (hit && counters && v.z < n_total) atomicAdd(&counters[v.z], 1u);
+            n_hit += hit;
         }
-        warp_add(placed, hit);
     }
+    warp_flush(placed, n_hit);
 }
 
 // ---- rebalance ---------------------------------------------------------------------------------------

@@ -25,16 +25,17 @@ p = R.GpuObjectPlacement(device=0)
 out = []
 
 
-def timed(fn, reps=5, warm=2):
+def timed(fn, reps=5, warm=2, prov=None):
+    prov = prov or p
     for _ in range(warm):
         fn()
-    p.sync()
-    p.event_record(0)
+    prov.sync()
+    prov.event_record(0)
     for _ in range(reps):
         fn()
-    p.event_record(1)
-    p.sync()
-    return p.event_elapsed_ms(0, 1) / reps
+    prov.event_record(1)
+    prov.sync()
+    return prov.event_elapsed_ms(0, 1) / reps
 
 
 def rec(name, ms, units, unit_name, bytes_=None, note=""):
@@ -96,7 +97,7 @@ s.commit()
 p2.sync()
 placed, slots = p2.directory_len()
 rec("directory upsert %dM keys (k_dir_upsert+finish, incl. growth)" % (nd // 1_000_000), (time.perf_counter() - t0) * 1e3, nd, "upserts", 36 * nd, "first commit: table grown/rehashed to %d slots" % slots)
-rec("directory upsert %dM keys steady (k_dir_upsert+finish)" % (nd // 1_000_000), timed(s.commit, 3, 1), nd, "upserts", 36 * nd)
+rec("directory upsert %dM keys steady (k_dir_upsert+finish)" % (nd // 1_000_000), timed(s.commit, 3, 1, p2), nd, "upserts", 36 * nd)
 keys_h, _ = s.read(0, min(nd, 20_000_000), want_keys=True)
 L = p2.L
 import ctypes as C
@@ -106,9 +107,9 @@ p2._ck(L.rio_cuda_dev_alloc(p2.h, nq * 8, C.byref(dk)))
 p2._ck(L.rio_cuda_dev_alloc(p2.h, nq * 4, C.byref(do)))
 p2._ck(L.rio_cuda_memcpy_h2d(p2.h, dk, keys_h.ctypes.data_as(C.c_void_p), nq * 8))
 p2.sync()
-rec("directory lookup %dM keys resident (k_dir_lookup)" % (nq // 1_000_000), timed(lambda: p2._ck(L.rio_cuda_lookup_batch_dev(p2.h, dk, nq, do)), 5, 2), nq, "lookups", 28 * nq,
+rec("directory lookup %dM keys resident (k_dir_lookup)" % (nq // 1_000_000), timed(lambda: p2._ck(L.rio_cuda_lookup_batch_dev(p2.h, dk, nq, do)), 5, 2, p2), nq, "lookups", 28 * nq,
     "28 B algorithmic; ~44 B at 32 B-sector granularity")
-ms = timed(lambda: p2.directory_len(), 3, 1)
+ms = timed(lambda: p2.directory_len(), 3, 1, p2)
 rec("directory scan %d slots (k_dir_count)" % slots, ms, slots, "slots", 16 * slots)
 t0 = time.perf_counter()
 removed = p2.clean_node(5)
