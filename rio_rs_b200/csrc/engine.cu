@@ -138,6 +138,7 @@ struct rio_placement {
     uint64_t dir_cap = 0;
     uint64_t dir_keys = 0;      // distinct keys claimed (exact after every host-synchronous call)
     uint64_t dir_keys_pending = 0;  // pessimistic additions from _dev upserts not yet reconciled
+    uint32_t dir_seq = 0;           // upsert sequence numbers handed out so far (ordering of duplicate keys, k_dir_upsert)
 
     DevBuf s_keys, s_idx, s_idx2, s_sel, s_slots, s_keys2, s_feats, s_packed, s_offsets, s_cost, s_misc, s_flush, s_gather;
     unsigned long long *d_scalars = nullptr;   // S_COUNT u64 + error u32
@@ -317,14 +318,20 @@ void dir_reserve(rio_placement *h, uint64_t n_more) {
     CUDA_TRY(cudaFreeAsync(h->dir.slots, h->stream));
     h->dir = nd;
     h->dir_cap = new_cap;
+    h->dir_seq = 0;   // the rehash copied node indices only
     check_device_error(h);
     reconcile_dir_keys(h);   // unplaced keys were dropped by the rehash
 }
 
 void dir_upsert_dev(rio_placement *h, const uint64_t *d_keys, const uint32_t *d_idx, uint32_t const_idx, uint64_t n) {
     if (!n) return;
-    h->s_slots.ensure(n * 8, h->stream);
-    launch_dir_upsert(h->L(), h->dir, d_keys, d_idx, const_idx, n, h->s_slots.as<uint64_t>(), h->d_scalars + S_NEWKEYS, h->d_error());
+    REQUIRE(n < 0xFFFFFFF0ull, "upsert batch too large");
+    if ((uint64_t)h->dir_seq + n + 1 > 0xFFFFFFFFull) {   // sequence space exhausted: one streaming pass resets it
+        launch_dir_clear_seq(h->L(), h->dir);
+        h->dir_seq = 0;
+    }
+    launch_dir_upsert(h->L(), h->dir, d_keys, d_idx, const_idx, n, h->dir_seq, h->d_scalars + S_NEWKEYS, h->d_error());
+    h->dir_seq += (uint32_t)n;
 }
 
 // ---- counter exchange: the single collective of the path (all-gather of M u32 per rank, then a sum) -------------

@@ -120,6 +120,7 @@ struct UmmaParams {
     float *out_cost;          // nullable
     uint32_t *counters;       // nullable
     uint32_t lbo_a, sbo_a, lbo_b, sbo_b;   // descriptor strides in bytes
+    uint32_t node_rows_in_smem;            // 1: fp32 node rows are also staged in shared memory for the resolve step
 };
 
 template <int NT, int LDW>
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
     unsigned char *sB = smem + kBarBytes;                          // 3 blocks of m_pad*32 bytes
     const uint32_t b_block_bytes = P.m_pad * 32;
     unsigned char *sA = sB + 3 * b_block_bytes;                    // kStages stages of 3 blocks
+    float *sN = reinterpret_cast<float *>(sA + kStages * kAStageBytes);   // m_pad x 16 fp32 (only when node_rows_in_smem)
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t n_tiles = P.m_pad / NT;
@@ -154,6 +156,10 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
 #pragma unroll
         for (int q = 0; q < 4; q++) { const float4 v = __ldg(row + q); f[4 * q] = v.x; f[4 * q + 1] = v.y; f[4 * q + 2] = v.z; f[4 * q + 3] = v.w; }
         store_row_split(sB, b_block_bytes, P.m_pad * 16, p, f);
+        if (P.node_rows_in_smem) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) reinterpret_cast<float4 *>(sN + (size_t)p * 16)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+        }
     }
     fence_proxy_async();
     tc_fence_before();
@@ -216,9 +222,18 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
         const uint32_t q = warp & 3;                    // TMEM lane quarter this warp may access
         const uint32_t lane_base = (q * 32) << 16;
         uint32_t it = 0, g = 0;
+        const float *nrows = P.node_rows_in_smem ? sN : P.fnode_c;   // generic pointer: shared or global
         for (uint64_t rb = blockIdx.x; rb < n_rb; rb += gridDim.x, it++) {
             float best = -INFINITY;
             uint32_t bgroup = 0;
+            // this thread's own object row, requested now so that its latency hides behind the tile loop
+            const uint64_t row = rb * kRows + q * 32 + lane;
+            float fo[16];
+            {
+                const float4 *src = reinterpret_cast<const float4 *>(P.fobj + (row < P.n ? row : 0) * 16);
+#pragma unroll
+                for (int w = 0; w < 4; w++) { const float4 x = __ldg(src + w); fo[4 * w] = x.x; fo[4 * w + 1] = x.y; fo[4 * w + 2] = x.z; fo[4 * w + 3] = x.w; }
+            }
             for (uint32_t t = 0; t < n_tiles; t++, g++) {
                 const uint32_t buf = g & 1, pht = (g >> 1) & 1;
                 mbar_wait(&t_full[buf], pht);
@@ -248,21 +263,17 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
                 mbar_arrive(&t_empty[buf]);
             }
             // resolve: the 8 candidates of the winning group, re-evaluated in fp32 with the CUDA-core kernel's fmaf order
-            const uint64_t row = rb * kRows + q * 32 + lane;
             if (row < P.n) {
-                float fo[16];
-                const float4 *src = reinterpret_cast<const float4 *>(P.fobj + row * 16);
-#pragma unroll
-                for (int w = 0; w < 4; w++) { const float4 x = __ldg(src + w); fo[4 * w] = x.x; fo[4 * w + 1] = x.y; fo[4 * w + 2] = x.z; fo[4 * w + 3] = x.w; }
                 float bc = 0.f; uint32_t bp = kNone;
+#pragma unroll 2
                 for (uint32_t cnd = 0; cnd < 8; cnd++) {
                     const uint32_t p = bgroup * 8 + cnd;
                     if (p >= P.n_live) break;
-                    const float4 *nr = reinterpret_cast<const float4 *>(P.fnode_c + (size_t)p * 16);
+                    const float4 *nr = reinterpret_cast<const float4 *>(nrows + (size_t)p * 16);
                     float acc = 0.f;
 #pragma unroll
                     for (int w = 0; w < 4; w++) {
-                        const float4 x = __ldg(nr + w);
+                        const float4 x = nr[w];
                         acc = fmaf(fo[4 * w + 0], x.x, acc); acc = fmaf(fo[4 * w + 1], x.y, acc);
                         acc = fmaf(fo[4 * w + 2], x.z, acc); acc = fmaf(fo[4 * w + 3], x.w, acc);
                     }
@@ -300,8 +311,10 @@ bool launch_assign_affinity_umma(const Launch &L, const float *d_fobj, uint64_t 
     if ((!small && (m_pad % 256)) || m_pad > affinity_umma_max_nodes()) return false;
     // K-major interleaved operands: LBO = distance between the two 16-byte K chunks, SBO = distance between 8-row groups
     // (confirmed on hardware: profiles/r01_umma_first_light.txt)
-    UmmaParams P{d_fobj, n, d_fnode_c, d_nidx_map, n_live, m_pad, d_out_idx, d_out_cost, d_counters, kRows * 16u, 128u, m_pad * 16u, 128u};
-    const size_t smem = kBarBytes + (size_t)3 * m_pad * 32 + (size_t)kStages * kAStageBytes;
+    size_t smem = kBarBytes + (size_t)3 * m_pad * 32 + (size_t)kStages * kAStageBytes;
+    const bool rows_in_smem = smem + (size_t)m_pad * 64 <= 227u * 1024u;
+    if (rows_in_smem) smem += (size_t)m_pad * 64;
+    UmmaParams P{d_fobj, n, d_fnode_c, d_nidx_map, n_live, m_pad, d_out_idx, d_out_cost, d_counters, kRows * 16u, 128u, m_pad * 16u, 128u, rows_in_smem ? 1u : 0u};
     const uint64_t n_rb = (n + kRows - 1) / kRows;
     const int grid = (int)(n_rb < (uint64_t)L.sm_count ? n_rb : (uint64_t)L.sm_count);
     const char *e = getenv("RIO_UMMA_LDW");   // TMEM loads in flight per wait (A/B runs): 1, 2 or 4 (default, profiles/r01_umma_ldw.txt)

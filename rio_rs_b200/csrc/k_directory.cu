@@ -62,16 +62,16 @@ k_dir_lookup(DirDev dir, const uint64_t *__restrict__ keys, uint64_t n, uint32_t
     }
 }
 
-// update (local.rs:22-40), batched.  Claim-or-find the slot with a 64-bit CAS on the key, then order duplicate keys of
-// the same batch with a 64-bit atomicMax on (seq << 32 | node): seq = position + 1, so the last one in array order wins.
-// k_dir_upsert_finish then clears seq.
+// update (local.rs:22-40), batched.  Claim-or-find the slot with a 64-bit CAS on the key, then order duplicate keys with a
+// 64-bit atomicMax on (seq << 32 | node): seq = seq_base + position + 1 grows monotonically across batches, so within a batch
+// the last one in array order wins and a later batch always beats an earlier one.  Readers look at the low word only.  When
+// the 32-bit sequence space is about to wrap the host runs k_dir_clear_seq once (a streaming pass).
 __global__ void __launch_bounds__(256)
-k_dir_upsert(DirDev dir, const uint64_t *__restrict__ keys, const uint32_t *__restrict__ idx, uint32_t const_idx, uint64_t n,
-             uint64_t *__restrict__ slot_scratch, unsigned long long *new_keys, uint32_t *error) {
+k_dir_upsert(DirDev dir, const uint64_t *__restrict__ keys, const uint32_t *__restrict__ idx, uint32_t const_idx, uint64_t n, uint32_t seq_base,
+             unsigned long long *new_keys, uint32_t *error) {
     unsigned long long n_fresh = 0;
     for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t i = base + threadIdx.x;
-        bool fresh = false;
         if (i < n) {
             const unsigned long long key = norm_key(__ldg(keys + i));
             const uint32_t node = idx ? __ldg(idx + i) : const_idx;
@@ -81,29 +81,21 @@ k_dir_upsert(DirDev dir, const uint64_t *__restrict__ keys, const uint32_t *__re
                 unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(&dir.slots[s].key);
                 if (k == kEmptyKey) {
                     k = atomicCAS(&dir.slots[s].key, kEmptyKey, key);
-                    if (k == kEmptyKey) { fresh = true; k = key; }
+                    if (k == kEmptyKey) { n_fresh++; k = key; }
                 }
                 if (k == key) { placed = true; break; }
                 s = (s + 1) & dir.mask;
             }
-            if (placed) {
-                atomicMax(&dir.slots[s].val, ((unsigned long long)(i + 1) << 32) | node);
-                slot_scratch[i] = s;
-            } else {
-                slot_scratch[i] = ~0ull;
-                atomicExch(error, 1u);   // table full: the host sizes the table so this cannot happen
-            }
+            if (placed) atomicMax(&dir.slots[s].val, ((unsigned long long)(seq_base + (uint32_t)i + 1u) << 32) | node);
+            else atomicExch(error, 1u);   // table full: the host sizes the table so this cannot happen
         }
-        n_fresh += fresh;
     }
     warp_flush(new_keys, n_fresh);   // whole warp reaches this point (the base loop is block-uniform)
 }
-__global__ void __launch_bounds__(256)
-k_dir_upsert_finish(DirDev dir, const uint64_t *__restrict__ slot_scratch, uint64_t n) {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t s = slot_scratch[i];
-        if (s != ~0ull) reinterpret_cast<uint32_t *>(&dir.slots[s].val)[1] = 0;   // idempotent for duplicates
-    }
+__global__ void __launch_bounds__(256) k_dir_clear_seq(DirDev dir) {
+    const uint64_t cap = dir.mask + 1;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x)
+        reinterpret_cast<uint32_t *>(&dir.slots[i].val)[1] = 0;
 }
 
 // clean_server (local.rs:51-58): streaming scan, the GPU analogue of retain(|_, v| *v != address)
@@ -190,10 +182,14 @@ k_dir_count(DirDev dir, unsigned long long *placed, uint32_t *counters, uint32_t
 __device__ __forceinline__ bool join_wins(uint64_t key, uint32_t cur, uint32_t new_idx, const uint4 nn, const uint4 *__restrict__ by_idx) {
     const ObjHash o = obj_hash(key);
     const uint32_t un = pair_hash(o, nn.x, nn.z, nn.w);
-    const uint64_t sn = (uint64_t)elog(un) * nn.y;
     const uint4 c = __ldg(by_idx + cur);
     if (c.y == 0) return true;   // incumbent is not live any more
     const uint32_t uc = pair_hash(o, c.x, c.z, c.w);
+    // cheap bracket first: E(u) lies in [clz(u) << 26, (clz(u)+1) << 26], so most comparisons (the new node wins only
+    // ~w/W of the time) are decided without evaluating the log polynomial at all
+    const uint32_t ln = clz_u32(un), lc = clz_u32(uc);
+    if ((uint64_t)(ln << 26) * nn.y > (uint64_t)((lc + 1u) << 26) * c.y) return false;
+    const uint64_t sn = (uint64_t)elog(un) * nn.y;
     const uint64_t sc = (uint64_t)elog(uc) * c.y;
     return cand_better(sn, un, new_idx, sc, uc, cur);
 }
@@ -239,16 +235,30 @@ k_dir_rebalance_join(DirDev dir, NodeTabDev tab, uint32_t new_idx, unsigned long
 // LEAVE(gone): pick the objects recorded on the node (4 B/object scan) into a compact list ...
 __global__ void __launch_bounds__(256)
 k_select_on_node(const uint32_t *__restrict__ idx, uint64_t n, uint32_t node, uint32_t *__restrict__ sel, unsigned long long *nsel) {
-    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t i = base + threadIdx.x;
-        const bool hit = i < n && __ldg(idx + i) == node;
-        const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
-        if (m) {
-            const unsigned lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    // 128-bit loads: one thread scans 4 consecutive objects (idx is allocated 256-byte aligned)
+    const uint64_t n4 = (n + 3) / 4;
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n4; base += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t v = base + threadIdx.x;
+        uint32_t hits = 0;   // bit q set: object 4v+q is on the node
+        if (v < n4) {
+            uint4 x;
+            if (4 * v + 3 < n) x = __ldg(reinterpret_cast<const uint4 *>(idx) + v);
+            else { x.x = __ldg(idx + 4 * v); x.y = 4 * v + 1 < n ? __ldg(idx + 4 * v + 1) : ~node; x.z = 4 * v + 2 < n ? __ldg(idx + 4 * v + 2) : ~node; x.w = ~node; }
+            hits = (x.x == node) | ((x.y == node) << 1) | ((x.z == node) << 2) | ((x.w == node) << 3);
+        }
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, hits != 0);
+        if (m) {                                        // rare: about 4/M of the vectors
+            const unsigned lane = threadIdx.x & 31;
+            const uint32_t mine = __popc(hits);
+            uint32_t pre = mine;                        // inclusive warp prefix sum of the hit counts
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, pre, o); if (lane >= (unsigned)o) pre += t; }
+            const uint32_t total = __shfl_sync(0xFFFFFFFFu, pre, 31);
             unsigned long long b = 0;
-            if (lane == leader) b = atomicAdd(nsel, (unsigned long long)__popc(m));
-            b = __shfl_sync(0xFFFFFFFFu, b, leader);
-            if (hit) sel[b + __popc(m & ((1u << lane) - 1))] = (uint32_t)i;
+            if (lane == 0) b = atomicAdd(nsel, (unsigned long long)total);
+            b = __shfl_sync(0xFFFFFFFFu, b, 0) + (pre - mine);
+#pragma unroll
+            for (int q = 0; q < 4; q++) if (hits >> q & 1) sel[b++] = (uint32_t)(4 * v + q);
         }
     }
 }
@@ -364,13 +374,14 @@ void launch_dir_lookup(const Launch &L, const DirDev &dir, const uint64_t *d_key
     k_dir_lookup<<<grid_for(n, 256, L.sm_count, 8), 256, 0, L.stream>>>(dir, d_keys, n, d_out);
     RIO_COUNT_LAUNCH(L);
 }
-void launch_dir_upsert(const Launch &L, const DirDev &dir, const uint64_t *d_keys, const uint32_t *d_idx, uint32_t const_idx, uint64_t n,
-                       uint64_t *d_slot_scratch, unsigned long long *d_new_keys, uint32_t *d_error) {
+void launch_dir_upsert(const Launch &L, const DirDev &dir, const uint64_t *d_keys, const uint32_t *d_idx, uint32_t const_idx, uint64_t n, uint32_t seq_base,
+                       unsigned long long *d_new_keys, uint32_t *d_error) {
     if (!n) return;
-    const int grid = grid_for(n, 256, L.sm_count, 8);
-    k_dir_upsert<<<grid, 256, 0, L.stream>>>(dir, d_keys, d_idx, const_idx, n, d_slot_scratch, d_new_keys, d_error);
+    k_dir_upsert<<<grid_for(n, 256, L.sm_count, 8), 256, 0, L.stream>>>(dir, d_keys, d_idx, const_idx, n, seq_base, d_new_keys, d_error);
     RIO_COUNT_LAUNCH(L);
-    k_dir_upsert_finish<<<grid, 256, 0, L.stream>>>(dir, d_slot_scratch, n);
+}
+void launch_dir_clear_seq(const Launch &L, const DirDev &dir) {
+    k_dir_clear_seq<<<grid_for(dir.mask + 1, 256, L.sm_count, 8), 256, 0, L.stream>>>(dir);
     RIO_COUNT_LAUNCH(L);
 }
 void launch_dir_clean_node(const Launch &L, const DirDev &dir, uint32_t node, unsigned long long *d_removed) {
@@ -405,7 +416,7 @@ void launch_rebalance_join(const Launch &L, const uint64_t *d_keys, uint32_t *d_
 }
 void launch_select_on_node(const Launch &L, const uint32_t *d_idx, uint64_t n, uint32_t node, uint32_t *d_sel, unsigned long long *d_nsel) {
     if (!n) return;
-    k_select_on_node<<<grid_for(n, 256, L.sm_count, 8), 256, 0, L.stream>>>(d_idx, n, node, d_sel, d_nsel);
+    k_select_on_node<<<grid_for((n + 3) / 4, 256, L.sm_count, 8), 256, 0, L.stream>>>(d_idx, n, node, d_sel, d_nsel);
     RIO_COUNT_LAUNCH(L);
 }
 void launch_select_spill(const Launch &L, const uint64_t *d_keys, const uint32_t *d_idx, uint64_t n, const uint32_t *d_thr, const uint8_t *d_over,

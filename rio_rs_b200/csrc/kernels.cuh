@@ -73,7 +73,8 @@ void launch_select_on_node(const Launch &L, const uint32_t *d_idx, uint64_t n, u
 void launch_dir_init(const Launch &L, DirSlot *slots, uint64_t cap);
 void launch_dir_lookup(const Launch &L, const DirDev &dir, const uint64_t *d_keys, uint64_t n, uint32_t *d_out);
 void launch_dir_upsert(const Launch &L, const DirDev &dir, const uint64_t *d_keys, const uint32_t *d_idx /*nullable => const_idx*/, uint32_t const_idx,
-                       uint64_t n, uint64_t *d_slot_scratch, unsigned long long *d_new_keys, uint32_t *d_error);
+                       uint64_t n, uint32_t seq_base, unsigned long long *d_new_keys, uint32_t *d_error);
+void launch_dir_clear_seq(const Launch &L, const DirDev &dir);
 void launch_dir_clean_node(const Launch &L, const DirDev &dir, uint32_t node, unsigned long long *d_removed);
 void launch_dir_clean_flagged(const Launch &L, const DirDev &dir, const uint8_t *d_flag, uint32_t n_total, unsigned long long *d_removed);
 void launch_dir_rehash(const Launch &L, const DirDev &from, const DirDev &to, unsigned long long *d_new_keys, uint32_t *d_error);
