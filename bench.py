@@ -43,6 +43,15 @@ ALGO_BYTES_PER_OBJECT = 12  # 8 B key read + 4 B node index written
 HBM_FALLBACK_GBS = 6650.0
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the assign kernel from the committed ncu capture."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_assign_v2.json")
+    try:
+        return float(json.load(open(p))["dram_bytes_per_launch"]), os.path.relpath(p, ROOT)
+    except Exception:
+        return None, None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -251,6 +260,7 @@ def main():
     p.sync()
     kern_ms = p.event_elapsed_ms(2, 3) / args.steps
     peak, peak_src = measured_peaks()
+    traffic, traffic_src = ncu_traffic() if (n == N_OBJECTS and M == N_NODES) else (None, None)
     achieved_gbs = ALGO_BYTES_PER_OBJECT * n / (kern_ms * 1e-3) / 1e9
     pair_rate = n * M / (kern_ms * 1e-3)
     mix_peak = max(p.bench_mix_rate(4000) for _ in range(3))
@@ -302,7 +312,7 @@ def main():
                        "objects_per_gpu": n, "global_objects": n_global, "nodes": M, "weights": "u32 in [1,16], seed 7", "capacity": "1.25", "max_rounds": 4,
                        "passes_run": passes, "l2": "inputs larger than L2: %d resident key sets rotated step to step" % N_SETS, "parallelism": "id-range shard x%d" % world,
                        "device": info["name"], "sms": info["sm_count"]},
-            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peak, "unit": "GB/s", "frac": achieved_gbs / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peak, "unit": "GB/s", "frac": achieved_gbs / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": "k_assign_hrw_v2", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_OBJECT * n, "peak_source": peak_src,
                          "note": "integer-ALU bound by construction (1024 pair hashes per 12 B); see alu_roofline"},
             "alu_roofline": {"bound": "int-alu", "achieved": pair_rate, "peak": mix_peak, "unit": "pair-hashes/s", "frac": pair_rate / mix_peak,
