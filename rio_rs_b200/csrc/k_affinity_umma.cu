@@ -7,14 +7,15 @@
 // (hh, hm, mh, mm, hl, lh; the dropped terms are <= 2^-24 relative), each term ONE tcgen05.mma (M=128 objects x
 // N=NT nodes x K=16) accumulating in fp32 in TMEM.  Nothing is materialised in HBM: the N x M grid lives only in TMEM.
 //
-// Warp roles (288 threads, one CTA per SM, persistent over 128-object row blocks):
-//   warps 0-3  producers : load 128 object rows (fp32, coalesced), split to bf16 h/m/l, store the three K-major
+// Warp roles (256 threads, one CTA per SM, persistent over 128-object row blocks):
+//   warps 0-1  producers : load 128 object rows (fp32, two per thread), split to bf16 h/m/l, store the three K-major
 //                          16-byte-interleaved operand blocks into shared memory, fence.proxy.async, arrive a_full
-//   warp  8    MMA issuer: one lane issues 6 tcgen05.mma per node tile into one of two TMEM accumulators,
+//   warp  2    MMA issuer: one lane issues 6 tcgen05.mma per node tile into one of two TMEM accumulators,
 //                          tcgen05.commit -> tmem_full (and -> a_empty after the last tile of the row block)
-//   warps 4-7  epilogue  : tcgen05.ld 32 columns at a time, 3-input max over groups of 8 columns, keep (best value,
-//                          best group); arrive tmem_empty; after the last tile re-evaluate the 8 candidates of the winning
-//                          group in fp32 (same fmaf order as the CUDA-core kernel) to get the index and the exact cost.
+//   warp  3    idle (keeps the epilogue on warps 4-7, whose warp%4 selects the TMEM lane quarter they may read)
+//   warps 4-7  epilogue  : double-buffered tcgen05.ld (64 columns per stage), 3-input max over groups of 8 columns, keep
+//                          (best value, best group); arrive tmem_empty; after the last tile re-evaluate the 8 candidates of the
+//                          winning group in fp32 (same fmaf order as the CUDA-core kernel): index + exact cost.
 // Node operands (3 bf16 blocks, 96 B per node) stay resident in shared memory for the whole kernel.
 #include "kernels.cuh"
 #include "spec.cuh"
@@ -26,7 +27,8 @@ namespace rio {
 
 namespace {
 
-constexpr int kUmmaThreads = 288;
+constexpr int kUmmaThreads = 256;   // 8 warps: a 9th warp would cap registers at 168/thread (3 warps on one SMSP)
+constexpr int kProducerThreads = 64;  // warps 0-1, two object rows per thread
 constexpr int kRows = 128;          // objects per row block == UMMA M
 constexpr int kStages = 2;          // A-operand stages
 constexpr uint32_t kABlockBytes = kRows * 32;            // one bf16 term of a row block: [2 k-chunks][128 rows][16 B]
@@ -142,11 +144,11 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
 
     // ---- one-time setup: barriers, TMEM, node operands ----------------------------------------------------------
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; s++) { mbar_init(&a_full[s], 128); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < kStages; s++) { mbar_init(&a_full[s], kProducerThreads); mbar_init(&a_empty[s], 1); }
         for (int b = 0; b < 2; b++) { mbar_init(&t_full[b], 1); mbar_init(&t_empty[b], 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) {
+    if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * NT)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -167,28 +169,31 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
-        // ===== producers: object rows -> bf16 h/m/l operand blocks =====
-        const uint32_t r = threadIdx.x;   // 0..127
+    if (warp < 2) {
+        // ===== producers: object rows -> bf16 h/m/l operand blocks (two rows per thread) =====
         uint32_t it = 0;
         for (uint64_t rb = blockIdx.x; rb < n_rb; rb += gridDim.x, it++) {
             const uint32_t s = it % kStages, ph = (it / kStages) & 1;
             mbar_wait(&a_empty[s], ph ^ 1);
-            const uint64_t row = rb * kRows + r;
-            float f[16];
-            if (row < P.n) {
-                const float4 *src = reinterpret_cast<const float4 *>(P.fobj + row * 16);
 #pragma unroll
-                for (int q = 0; q < 4; q++) { const float4 v = __ldg(src + q); f[4 * q] = v.x; f[4 * q + 1] = v.y; f[4 * q + 2] = v.z; f[4 * q + 3] = v.w; }
-            } else {
+            for (int half = 0; half < 2; half++) {
+                const uint32_t r = threadIdx.x + half * kProducerThreads;   // 0..127
+                const uint64_t row = rb * kRows + r;
+                float f[16];
+                if (row < P.n) {
+                    const float4 *src = reinterpret_cast<const float4 *>(P.fobj + row * 16);
 #pragma unroll
-                for (int k = 0; k < 16; k++) f[k] = 0.f;
+                    for (int q = 0; q < 4; q++) { const float4 v = __ldg(src + q); f[4 * q] = v.x; f[4 * q + 1] = v.y; f[4 * q + 2] = v.z; f[4 * q + 3] = v.w; }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 16; k++) f[k] = 0.f;
+                }
+                store_row_split(sA + s * kAStageBytes, kABlockBytes, kRows * 16, r, f);
             }
-            store_row_split(sA + s * kAStageBytes, kABlockBytes, kRows * 16, r, f);
             fence_proxy_async();             // generic-proxy stores -> visible to the tensor core (async proxy)
             mbar_arrive(&a_full[s]);
         }
-    } else if (warp == 8) {
+    } else if (warp == 2) {
         // ===== MMA issuer (one lane) =====
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
@@ -217,7 +222,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
             }
         }
         __syncwarp();
-    } else {
+    } else if (warp >= 4) {
         // ===== epilogue warps 4..7: TMEM -> registers -> running (best value, best group of 8 columns) =====
         const uint32_t q = warp & 3;                    // TMEM lane quarter this warp may access
         const uint32_t lane_base = (q * 32) << 16;
@@ -238,26 +243,35 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
                 const uint32_t buf = g & 1, pht = (g >> 1) & 1;
                 mbar_wait(&t_full[buf], pht);
                 tc_fence_after();
-#pragma unroll 1
-                for (uint32_t c0 = 0; c0 < NT / 32; c0 += LDW) {
-                    uint32_t v[LDW][32];
+                // double-buffered TMEM reads: the loads of stage s+1 are in flight while stage s is reduced
+                constexpr int kStagesPerTile = NT / (32 * LDW);
+                uint32_t v[2][LDW][32];
+                const uint32_t tcol = tmem_base + lane_base + buf * NT;
 #pragma unroll
-                    for (int w = 0; w < LDW; w++) tmem_ld32(tmem_base + lane_base + buf * NT + (c0 + w) * 32, v[w]);   // LDW loads in flight
-                    tmem_wait_ld();
+                for (int w = 0; w < LDW; w++) tmem_ld32(tcol + w * 32, v[0][w]);
+                tmem_wait_ld();
+#pragma unroll
+                for (int st = 0; st < kStagesPerTile; st++) {
+                    if (st + 1 < kStagesPerTile) {
+#pragma unroll
+                        for (int w = 0; w < LDW; w++) tmem_ld32(tcol + ((st + 1) * LDW + w) * 32, v[(st + 1) & 1][w]);
+                    }
 #pragma unroll
                     for (int w = 0; w < LDW; w++) {
-                        const uint32_t col0 = t * NT + (c0 + w) * 32;
+                        uint32_t (&x)[32] = v[st & 1][w];
+                        const uint32_t col0 = t * NT + (st * LDW + w) * 32;
                         if (col0 + 32 > P.n_live) {          // warp-uniform: only the padded tail of the last tile
 #pragma unroll
-                            for (int i = 0; i < 32; i++) if (col0 + i >= P.n_live) v[w][i] = 0xFF800000u;   // -inf
+                            for (int i = 0; i < 32; i++) if (col0 + i >= P.n_live) x[i] = 0xFF800000u;   // -inf
                         }
 #pragma unroll
                         for (int gq = 0; gq < 4; gq++) {
-                            const float *f = reinterpret_cast<const float *>(&v[w][gq * 8]);
+                            const float *f = reinterpret_cast<const float *>(&x[gq * 8]);
                             const float gm = fmaxf(max3f(max3f(f[0], f[1], f[2]), f[3], f[4]), max3f(f[5], f[6], f[7]));
                             if (gm > best) { best = gm; bgroup = (col0 >> 3) + gq; }
                         }
                     }
+                    if (st + 1 < kStagesPerTile) tmem_wait_ld();
                 }
                 tc_fence_before();
                 mbar_arrive(&t_empty[buf]);
@@ -291,7 +305,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
     // ---- teardown -------------------------------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * NT)) : "memory");
     }
@@ -317,20 +331,17 @@ bool launch_assign_affinity_umma(const Launch &L, const float *d_fobj, uint64_t 
     UmmaParams P{d_fobj, n, d_fnode_c, d_nidx_map, n_live, m_pad, d_out_idx, d_out_cost, d_counters, kRows * 16u, 128u, m_pad * 16u, 128u, rows_in_smem ? 1u : 0u};
     const uint64_t n_rb = (n + kRows - 1) / kRows;
     const int grid = (int)(n_rb < (uint64_t)L.sm_count ? n_rb : (uint64_t)L.sm_count);
-    const char *e = getenv("RIO_UMMA_LDW");   // TMEM loads in flight per wait (A/B runs): 1, 2 or 4 (default, profiles/r01_umma_ldw.txt)
-    const int ldw = e ? atoi(e) : 4;
+    const char *e = getenv("RIO_UMMA_LDW");   // x32 TMEM loads per double-buffer stage (A/B runs): 1 or 2 (default)
+    const int ldw = e ? atoi(e) : 2;
     if (small) {
-        cudaFuncSetAttribute(k_affinity_umma<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_affinity_umma<64, 2><<<grid, kUmmaThreads, smem, L.stream>>>(P);
+        cudaFuncSetAttribute(k_affinity_umma<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_affinity_umma<64, 1><<<grid, kUmmaThreads, smem, L.stream>>>(P);
     } else if (ldw == 1) {
         cudaFuncSetAttribute(k_affinity_umma<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k_affinity_umma<256, 1><<<grid, kUmmaThreads, smem, L.stream>>>(P);
-    } else if (ldw == 2) {
+    } else {   // (4 per stage needs 256 staging registers and spills: not compiled)
         cudaFuncSetAttribute(k_affinity_umma<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k_affinity_umma<256, 2><<<grid, kUmmaThreads, smem, L.stream>>>(P);
-    } else {
-        cudaFuncSetAttribute(k_affinity_umma<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_affinity_umma<256, 4><<<grid, kUmmaThreads, smem, L.stream>>>(P);
     }
     RIO_COUNT_LAUNCH(L);
     return true;

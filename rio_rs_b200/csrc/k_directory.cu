@@ -179,10 +179,10 @@ k_dir_count(DirDev dir, unsigned long long *placed, uint32_t *counters, uint32_t
 // JOIN(new): an object moves iff the new node beats its incumbent under the spec order (score, ~u, j); both
 // candidates are one pair hash each (the incumbent's is recomputed from (key, idx) instead of being stored, so
 // the stream is 12 B/object for a dense set, 16 B/slot for the directory).  by_idx[] gives {s0, invw, s2}.
-__device__ __forceinline__ bool join_wins(uint64_t key, uint32_t cur, uint32_t new_idx, const uint4 nn, const uint4 *__restrict__ by_idx) {
+__device__ __forceinline__ bool join_wins(uint64_t key, uint32_t cur, uint32_t new_idx, const uint4 nn, const uint4 *by_idx) {
     const ObjHash o = obj_hash(key);
     const uint32_t un = pair_hash(o, nn.x, nn.z, nn.w);
-    const uint4 c = __ldg(by_idx + cur);
+    const uint4 c = by_idx[cur];   // shared memory (staged) or global
     if (c.y == 0) return true;   // incumbent is not live any more
     const uint32_t uc = pair_hash(o, c.x, c.z, c.w);
     // cheap bracket first: E(u) lies in [clz(u) << 26, (clz(u)+1) << 26], so most comparisons (the new node wins only
@@ -194,9 +194,21 @@ __device__ __forceinline__ bool join_wins(uint64_t key, uint32_t cur, uint32_t n
     return cand_better(sn, un, new_idx, sc, uc, cur);
 }
 
+// The incumbent's node record is a random 16-byte gather: from L1 that costs one wavefront per distinct line (up to 32 per
+// warp load), so the by-index table is staged in shared memory when it fits (smem_nodes != 0).
+__device__ __forceinline__ const uint4 *stage_by_idx(const NodeTabDev &tab, uint32_t smem_nodes) {
+    extern __shared__ __align__(16) unsigned char smem_dir[];
+    if (!smem_nodes) return tab.by_idx;
+    uint4 *s = reinterpret_cast<uint4 *>(smem_dir);
+    for (uint32_t j = threadIdx.x; j < tab.n_total; j += blockDim.x) s[j] = __ldg(tab.by_idx + j);
+    __syncthreads();
+    return s;
+}
+
 __global__ void __launch_bounds__(256)
 k_rebalance_join(const uint64_t *__restrict__ keys, uint32_t *__restrict__ idx, uint64_t n, NodeTabDev tab, uint32_t new_idx,
-                 uint32_t *__restrict__ counters, unsigned long long *moved) {
+                 uint32_t *__restrict__ counters, unsigned long long *moved, uint32_t smem_nodes) {
+    const uint4 *by_idx = stage_by_idx(tab, smem_nodes);
     const uint4 nn = __ldg(tab.by_idx + new_idx);
     for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t i = base + threadIdx.x;
@@ -204,7 +216,7 @@ k_rebalance_join(const uint64_t *__restrict__ keys, uint32_t *__restrict__ idx, 
         if (i < n) {
             const uint32_t cur = idx[i];
             if (cur != new_idx && cur < tab.n_total && nn.y) {
-                mv = join_wins(__ldg(keys + i), cur, new_idx, nn, tab.by_idx);
+                mv = join_wins(__ldg(keys + i), cur, new_idx, nn, by_idx);
                 if (mv) { idx[i] = new_idx; if (counters) { atomicSub(&counters[cur], 1u); atomicAdd(&counters[new_idx], 1u); } }
             }
         }
@@ -213,7 +225,8 @@ k_rebalance_join(const uint64_t *__restrict__ keys, uint32_t *__restrict__ idx, 
 }
 
 __global__ void __launch_bounds__(256)
-k_dir_rebalance_join(DirDev dir, NodeTabDev tab, uint32_t new_idx, unsigned long long *moved) {
+k_dir_rebalance_join(DirDev dir, NodeTabDev tab, uint32_t new_idx, unsigned long long *moved, uint32_t smem_nodes) {
+    const uint4 *by_idx = stage_by_idx(tab, smem_nodes);
     const uint4 *slots = reinterpret_cast<const uint4 *>(dir.slots);
     const uint4 nn = __ldg(tab.by_idx + new_idx);
     const uint64_t cap = dir.mask + 1;
@@ -224,7 +237,7 @@ k_dir_rebalance_join(DirDev dir, NodeTabDev tab, uint32_t new_idx, unsigned long
             const uint4 v = slots[i];
             const unsigned long long key = ((unsigned long long)v.y << 32) | v.x;
             if (key != kEmptyKey && v.z != kNone && v.z != new_idx && v.z < tab.n_total && nn.y) {
-                mv = join_wins(key, v.z, new_idx, nn, tab.by_idx);
+                mv = join_wins(key, v.z, new_idx, nn, by_idx);
                 if (mv) reinterpret_cast<uint32_t *>(&dir.slots[i].val)[0] = new_idx;
             }
         }
@@ -401,7 +414,9 @@ void launch_dir_count(const Launch &L, const DirDev &dir, unsigned long long *d_
     RIO_COUNT_LAUNCH(L);
 }
 void launch_dir_rebalance_join(const Launch &L, const DirDev &dir, const NodeTabDev &tab, uint32_t new_idx, unsigned long long *d_moved) {
-    k_dir_rebalance_join<<<grid_for(dir.mask + 1, 256, L.sm_count, 8), 256, 0, L.stream>>>(dir, tab, new_idx, d_moved);
+    const uint32_t sn = tab.n_total <= 6144 ? tab.n_total : 0;   // 96 KB of node records at most
+    cudaFuncSetAttribute(k_dir_rebalance_join, cudaFuncAttributeMaxDynamicSharedMemorySize, 6144 * 16);
+    k_dir_rebalance_join<<<grid_for(dir.mask + 1, 256, L.sm_count, sn > 2048 ? 2 : 8), 256, (size_t)sn * 16, L.stream>>>(dir, tab, new_idx, d_moved, sn);
     RIO_COUNT_LAUNCH(L);
 }
 void launch_dir_rebalance_leave(const Launch &L, const DirDev &dir, const NodeTabDev &tab, uint32_t gone_idx, unsigned long long *d_moved) {
@@ -411,7 +426,9 @@ void launch_dir_rebalance_leave(const Launch &L, const DirDev &dir, const NodeTa
 void launch_rebalance_join(const Launch &L, const uint64_t *d_keys, uint32_t *d_idx, uint64_t n, const NodeTabDev &tab, uint32_t new_idx,
                            uint32_t *d_counters, unsigned long long *d_moved) {
     if (!n) return;
-    k_rebalance_join<<<grid_for(n, 256, L.sm_count, 8), 256, 0, L.stream>>>(d_keys, d_idx, n, tab, new_idx, d_counters, d_moved);
+    const uint32_t sn = tab.n_total <= 6144 ? tab.n_total : 0;
+    cudaFuncSetAttribute(k_rebalance_join, cudaFuncAttributeMaxDynamicSharedMemorySize, 6144 * 16);
+    k_rebalance_join<<<grid_for(n, 256, L.sm_count, sn > 2048 ? 2 : 8), 256, (size_t)sn * 16, L.stream>>>(d_keys, d_idx, n, tab, new_idx, d_counters, d_moved, sn);
     RIO_COUNT_LAUNCH(L);
 }
 void launch_select_on_node(const Launch &L, const uint32_t *d_idx, uint64_t n, uint32_t node, uint32_t *d_sel, unsigned long long *d_nsel) {

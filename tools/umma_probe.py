@@ -36,7 +36,7 @@ for (M, n) in [(1024, 100_000), (37, 5001), (300, 20_000)]:
         s.synth_keys(0, N, 1)
         big = np.random.default_rng(5).uniform(-1, 1, (N, 16)).astype(np.float32)
         s.load_feats(big)
-        for var, ldw in (("umma", "1"), ("umma", "2"), ("umma", "4"), ("ffma", "2")):
+        for var, ldw in (("umma", "1"), ("umma", "2"), ("ffma", "2")):
             os.environ["RIO_AFFINITY_VARIANT"] = var
             os.environ["RIO_UMMA_LDW"] = ldw
             s.assign(True); p.sync()
