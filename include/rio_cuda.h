@@ -92,6 +92,8 @@ rio_status  rio_cuda_node_upsert(rio_placement *h, const char *address, uint32_t
 /* set_active / set_inactive (peer_to_peer.rs:170-191, storage/mod.rs:112-120) */
 rio_status  rio_cuda_node_set_active(rio_placement *h, uint32_t idx, int32_t active);
 rio_status  rio_cuda_node_index(rio_placement *h, const char *address, uint32_t *out_idx); /* RIO_NONE if unknown */
+/* Intern an address without changing liveness (any address may be recorded by update, live or not: local.rs:34-36) */
+rio_status  rio_cuda_node_intern(rio_placement *h, const char *address, uint32_t *out_idx);
 rio_status  rio_cuda_node_address(rio_placement *h, uint32_t idx, char *buf, size_t cap, size_t *out_len);
 rio_status  rio_cuda_node_count(rio_placement *h, uint32_t *out_total, uint32_t *out_live);
 

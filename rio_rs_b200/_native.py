@@ -45,6 +45,7 @@ SIGNATURES = {
     "rio_cuda_node_upsert": (C.c_int32, [H, C.c_char_p, C.c_uint32, vp, C.c_uint32, u32p]),
     "rio_cuda_node_set_active": (C.c_int32, [H, C.c_uint32, C.c_int32]),
     "rio_cuda_node_index": (C.c_int32, [H, C.c_char_p, u32p]),
+    "rio_cuda_node_intern": (C.c_int32, [H, C.c_char_p, u32p]),
     "rio_cuda_node_address": (C.c_int32, [H, C.c_uint32, C.c_char_p, sz, C.POINTER(sz)]),
     "rio_cuda_node_count": (C.c_int32, [H, u32p, u32p]),
     "rio_cuda_lookup_batch": (C.c_int32, [H, vp, sz, vp]),

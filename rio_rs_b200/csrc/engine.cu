@@ -613,6 +613,14 @@ rio_status rio_cuda_node_index(rio_placement *h, const char *address, uint32_t *
     });
 }
 
+rio_status rio_cuda_node_intern(rio_placement *h, const char *address, uint32_t *out_idx) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] {
+        REQUIRE(address && out_idx, "null argument");
+        *out_idx = intern_node(h, address);
+    });
+}
+
 rio_status rio_cuda_node_address(rio_placement *h, uint32_t idx, char *buf, size_t cap, size_t *out_len) {
     if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
     return guarded(h, [&] {

@@ -156,6 +156,11 @@ class GpuObjectPlacement:
         self._ck(self.L.rio_cuda_node_index(self.h, address.encode(), C.byref(idx)))
         return None if idx.value == N.NONE else idx.value
 
+    def node_intern(self, address):
+        idx = C.c_uint32(0)
+        self._ck(self.L.rio_cuda_node_intern(self.h, address.encode(), C.byref(idx)))
+        return idx.value
+
     def node_address(self, idx):
         n = C.c_size_t(0)
         self._ck(self.L.rio_cuda_node_address(self.h, idx, self._buf, 512, C.byref(n)))

@@ -22,6 +22,10 @@ pub struct rio_objset {
     _private: [u8; 0],
 }
 #[repr(C)]
+pub struct rio_resolver {
+    _private: [u8; 0],
+}
+#[repr(C)]
 #[derive(Clone, Copy, Default)]
 pub struct rio_config {
     pub struct_size: u32,
@@ -47,6 +51,7 @@ extern "C" {
     pub fn rio_cuda_node_upsert(h: *mut rio_placement, address: *const c_char, weight: u32, feat: *const f32, k: u32, out_idx: *mut u32) -> rio_status;
     pub fn rio_cuda_node_set_active(h: *mut rio_placement, idx: u32, active: i32) -> rio_status;
     pub fn rio_cuda_node_index(h: *mut rio_placement, address: *const c_char, out_idx: *mut u32) -> rio_status;
+    pub fn rio_cuda_node_intern(h: *mut rio_placement, address: *const c_char, out_idx: *mut u32) -> rio_status;
     pub fn rio_cuda_node_address(h: *mut rio_placement, idx: u32, buf: *mut c_char, cap: size_t, out_len: *mut size_t) -> rio_status;
     pub fn rio_cuda_node_count(h: *mut rio_placement, out_total: *mut u32, out_live: *mut u32) -> rio_status;
 
@@ -94,6 +99,13 @@ extern "C" {
     pub fn rio_cuda_event_elapsed_ms(h: *mut rio_placement, a: u32, b: u32, out_ms: *mut f32) -> rio_status;
     pub fn rio_cuda_bench_mix_rate(h: *mut rio_placement, iters: u32, out_pairs_per_s: *mut f64) -> rio_status;
     pub fn rio_cuda_launch_count(h: *mut rio_placement, out: *mut u64) -> rio_status;
+
+    pub fn rio_cuda_resolver_create(h: *mut rio_placement, policy: u32, self_idx: u32, max_batch: u32, max_wait_us: u32, out: *mut *mut rio_resolver) -> rio_status;
+    pub fn rio_cuda_resolver_destroy(r: *mut rio_resolver);
+    pub fn rio_cuda_resolver_resolve(r: *mut rio_resolver, key: u64, out_idx: *mut u32) -> rio_status;
+    pub fn rio_cuda_resolver_resolve_str(r: *mut rio_resolver, ty: *const c_char, ty_len: size_t, id: *const c_char, id_len: size_t, buf: *mut c_char, cap: size_t, out_len: *mut size_t) -> rio_status;
+    pub fn rio_cuda_resolver_stats(r: *mut rio_resolver, calls: *mut u64, batches: *mut u64, largest_batch: *mut u64) -> rio_status;
+    pub fn rio_cuda_resolver_last_error() -> *const c_char;
 
     pub fn rio_cuda_update_str(h: *mut rio_placement, ty: *const c_char, ty_len: size_t, id: *const c_char, id_len: size_t, address: *const c_char, address_len: size_t) -> rio_status;
     pub fn rio_cuda_lookup_str(h: *mut rio_placement, ty: *const c_char, ty_len: size_t, id: *const c_char, id_len: size_t, buf: *mut c_char, cap: size_t, out_len: *mut size_t) -> rio_status;

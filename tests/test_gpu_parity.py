@@ -492,3 +492,39 @@ def test_resolver_coalesces_concurrent_per_id_calls(gp, oracle):
     keys = oracle.synth_keys(300, 2)
     assert [r3.resolve(int(k)) for k in keys] == oracle.assign_hrw(keys, seeds, w).tolist()
     r.close(); r2.close(); r3.close()
+
+
+# ---- durable write-through into the reference's SQL schema ----------------------------------------
+def test_durable_write_through_and_recovery(gp, oracle, tmp_path):
+    """Mutations go to the GPU directory AND the reference's sqlite table (sqlite.rs:68-126 statements); a fresh provider
+    pointed at the same file recovers every placement (bulk path: device-side id hashing + batched upsert), and the
+    table itself equals the SqliteObjectPlacement restatement fed the same ops."""
+    from oracle.sqlite_model import SqliteDirectoryModel
+    from rio_rs_b200.durable import DurableGpuObjectPlacement
+
+    db = str(tmp_path / "placement.sqlite3")
+    p = DurableGpuObjectPlacement(db)
+    assert p.prepare() == 0
+    m = SqliteDirectoryModel()
+    m.prepare()
+    addrs = ["10.0.0.%d:5000" % j for j in range(5)]
+    ids = [("Obj", str(i)) for i in range(3000)]
+    tgt = [addrs[i % 5] for i in range(3000)]
+    p.update_many_ids(ids, tgt)
+    for (t, i), a in zip(ids, tgt):
+        m.update(t, i, a)
+    p.update(gp.ObjectPlacementItem(gp.ObjectId("Obj", "7"), "10.0.0.4:5000"))
+    m.update("Obj", "7", "10.0.0.4:5000")
+    p.remove(gp.ObjectId("Obj", "8"))
+    m.remove("Obj", "8")
+    p.clean_server(addrs[2])
+    m.clean_server(addrs[2])
+    del p
+    q = DurableGpuObjectPlacement(db)   # "restart"
+    restored = q.prepare()
+    want = {(t, i): m.lookup(t, i) for t, i in ids}
+    assert restored == sum(1 for v in want.values() if v is not None)
+    for k in range(0, 3000, 13):
+        assert q.lookup(gp.ObjectId(*ids[k])) == want[ids[k]]
+    assert q.lookup(gp.ObjectId("Obj", "7")) == "10.0.0.4:5000" and q.lookup(gp.ObjectId("Obj", "8")) is None
+    assert q.directory_len()[0] == restored
