@@ -43,22 +43,41 @@ __global__ void k_dir_init(DirSlot *slots, uint64_t cap) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) p[i] = e;
 }
 
-// lookup (local.rs:42-49)
+// lookup (local.rs:42-49).  Random 16-byte probes are latency bound (ncu: long_scoreboard), so every thread keeps four
+// independent first probes in flight; the rare longer probe sequences are finished one by one afterwards.
+constexpr int kLookupIlp = 4;
 __global__ void __launch_bounds__(256)
 k_dir_lookup(DirDev dir, const uint64_t *__restrict__ keys, uint64_t n, uint32_t *__restrict__ out) {
     const uint4 *slots = reinterpret_cast<const uint4 *>(dir.slots);
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const unsigned long long key = norm_key(__ldg(keys + i));
-        uint64_t s = home_slot(key, dir);
-        uint32_t res = kNone;
-        for (uint64_t probes = 0; probes <= dir.mask; probes++) {
-            const uint4 v = slots[s];   // one 16-byte load: key + value together
-            const unsigned long long k = ((unsigned long long)v.y << 32) | v.x;
-            if (k == key) { res = v.z; break; }
-            if (k == kEmptyKey) break;
-            s = (s + 1) & dir.mask;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += stride * kLookupIlp) {
+        unsigned long long key[kLookupIlp];
+        uint64_t s[kLookupIlp];
+        uint4 v[kLookupIlp];
+#pragma unroll
+        for (int q = 0; q < kLookupIlp; q++) {
+            const uint64_t i = i0 + q * stride;
+            key[q] = norm_key(i < n ? __ldg(keys + i) : 0);
+            s[q] = home_slot(key[q], dir);
         }
-        out[i] = res;
+#pragma unroll
+        for (int q = 0; q < kLookupIlp; q++) v[q] = slots[s[q]];   // four independent 16-byte probes in flight
+#pragma unroll
+        for (int q = 0; q < kLookupIlp; q++) {
+            const uint64_t i = i0 + q * stride;
+            if (i >= n) continue;
+            uint32_t res = kNone;
+            uint4 x = v[q];
+            uint64_t sl = s[q];
+            for (uint64_t probes = 0; probes <= dir.mask; probes++) {
+                const unsigned long long k = ((unsigned long long)x.y << 32) | x.x;
+                if (k == key[q]) { res = x.z; break; }
+                if (k == kEmptyKey) break;
+                sl = (sl + 1) & dir.mask;
+                x = slots[sl];
+            }
+            out[i] = res;
+        }
     }
 }
 
@@ -384,7 +403,7 @@ void launch_dir_init(const Launch &L, DirSlot *slots, uint64_t cap) {
 }
 void launch_dir_lookup(const Launch &L, const DirDev &dir, const uint64_t *d_keys, uint64_t n, uint32_t *d_out) {
     if (!n) return;
-    k_dir_lookup<<<grid_for(n, 256, L.sm_count, 8), 256, 0, L.stream>>>(dir, d_keys, n, d_out);
+    k_dir_lookup<<<grid_for((n + kLookupIlp - 1) / kLookupIlp, 256, L.sm_count, 8), 256, 0, L.stream>>>(dir, d_keys, n, d_out);
     RIO_COUNT_LAUNCH(L);
 }
 void launch_dir_upsert(const Launch &L, const DirDev &dir, const uint64_t *d_keys, const uint32_t *d_idx, uint32_t const_idx, uint64_t n, uint32_t seq_base,
