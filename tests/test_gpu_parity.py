@@ -528,3 +528,54 @@ def test_durable_write_through_and_recovery(gp, oracle, tmp_path):
         assert q.lookup(gp.ObjectId(*ids[k])) == want[ids[k]]
     assert q.lookup(gp.ObjectId("Obj", "7")) == "10.0.0.4:5000" and q.lookup(gp.ObjectId("Obj", "8")) is None
     assert q.directory_len()[0] == restored
+
+
+# ---- device-side id hashing and the device-resident (_dev) entry points ---------------------------------------------
+def test_hash_ids_ragged_lengths(gp, oracle):
+    """FNV-1a over the joined "{type}.{id}" bytes on the GPU == rio_cuda_object_key == oracle, for empty, short and very
+    long ids (longer than the kernel's shared-memory staging window)."""
+    rng = random.Random(5)
+    ids = [("", ""), ("a.b", "c"), ("a", "b.c"), ("T", "x" * 70000)]
+    for _ in range(5000):
+        ids.append(("T%d" % rng.randrange(5), "".join(rng.choice("abcdef0123456789-") for _ in range(rng.choice([0, 1, 3, 8, 13, 36, 200])))))
+    p = provider(gp)
+    got = p.hash_ids(ids)
+    assert got.tolist() == [oracle.object_key(t, i) for t, i in ids]
+    assert got[1] == got[2]   # the reference's own aliasing of ("a.b","c") and ("a","b.c") (local.rs:26-29)
+    assert p.hash_ids([]).shape == (0,)
+
+
+def test_device_resident_entry_points(gp, oracle):
+    """rio_cuda_*_dev: inputs already in HBM, asynchronous on the engine stream (what bench.py's `value` path uses)."""
+    import ctypes as C
+
+    p = provider(gp)
+    addrs, seeds, w = oracle.synth_nodes(50)
+    p.set_nodes(addrs, w)
+    n = 123457
+    keys = oracle.synth_keys(n, 3)
+    L, h = p.L, p.h
+    dk, di, dl = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    for ptr, nbytes in ((dk, n * 8), (di, n * 4), (dl, n * 4)):
+        p._ck(L.rio_cuda_dev_alloc(h, nbytes, C.byref(ptr)))
+    p._ck(L.rio_cuda_memcpy_h2d(h, dk, keys.ctypes.data_as(C.c_void_p), n * 8))
+    p._ck(L.rio_cuda_assign_batch_dev(h, dk, None, n, di))
+    p._ck(L.rio_cuda_directory_reserve(h, n))
+    p._ck(L.rio_cuda_upsert_batch_dev(h, dk, di, n))
+    p._ck(L.rio_cuda_lookup_batch_dev(h, dk, n, dl))
+    out_i, out_l = np.empty(n, dtype=np.uint32), np.empty(n, dtype=np.uint32)
+    p._ck(L.rio_cuda_memcpy_d2h(h, out_i.ctypes.data_as(C.c_void_p), di, n * 4))
+    p._ck(L.rio_cuda_memcpy_d2h(h, out_l.ctypes.data_as(C.c_void_p), dl, n * 4))
+    p.sync()
+    want = oracle.assign_hrw(keys, seeds, w, threads=4)
+    assert (out_i == want).all() and (out_l == want).all()
+    assert p.directory_len()[0] == n
+    for ptr in (dk, di, dl):
+        p._ck(L.rio_cuda_dev_free(h, ptr))
+    # an undersized table is refused up front instead of overflowing asynchronously
+    q = provider(gp, directory_capacity=1024)
+    q.set_nodes(addrs, w)
+    q._ck(L.rio_cuda_dev_alloc(q.h, n * 8, C.byref(dk)))
+    q._ck(L.rio_cuda_dev_alloc(q.h, n * 4, C.byref(di)))
+    with pytest.raises(gp.Unknown):
+        q._ck(L.rio_cuda_upsert_batch_dev(q.h, dk, di, n))
