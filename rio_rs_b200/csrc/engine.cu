@@ -1133,6 +1133,11 @@ rio_status rio_cuda_bench_mix_rate(rio_placement *h, uint32_t iters, double *out
         *out_pairs_per_s = (double)pairs / ((double)ms * 1e-3);
     });
 }
+/* development hook, deliberately not in include/rio_cuda.h: per-role cycle counters of the tcgen05 affinity kernel */
+rio_status rio_dev_umma_timing(rio_placement *h, unsigned long long *d_buf) {
+    if (!h) return RIO_ERR_UNKNOWN;
+    return guarded(h, [&] { CUDA_TRY(cudaStreamSynchronize(h->stream)); affinity_umma_set_timing_buffer(d_buf); });
+}
 rio_status rio_cuda_event_record(rio_placement *h, uint32_t slot) {
     if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
     return guarded(h, [&] { REQUIRE(slot < RIO_MAX_EVENTS, "event slot out of range"); CUDA_TRY(cudaEventRecord(h->events[slot], h->stream)); });

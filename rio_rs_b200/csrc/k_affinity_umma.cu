@@ -123,6 +123,7 @@ struct UmmaParams {
     uint32_t *counters;       // nullable
     uint32_t lbo_a, sbo_a, lbo_b, sbo_b;   // descriptor strides in bytes
     uint32_t node_rows_in_smem;            // 1: fp32 node rows are also staged in shared memory for the resolve step
+    unsigned long long *timing;            // optional per-CTA cycle counters (16 per CTA) for tools/umma_timing.py; NULL in production
 };
 
 template <int NT, int LDW>
@@ -172,9 +173,12 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
     if (warp < 2) {
         // ===== producers: object rows -> bf16 h/m/l operand blocks (two rows per thread) =====
         uint32_t it = 0;
+        long long tw = 0, tk = 0;
         for (uint64_t rb = blockIdx.x; rb < n_rb; rb += gridDim.x, it++) {
             const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+            const long long c0 = P.timing ? clock64() : 0;
             mbar_wait(&a_empty[s], ph ^ 1);
+            const long long c1 = P.timing ? clock64() : 0;
 #pragma unroll
             for (int half = 0; half < 2; half++) {
                 const uint32_t r = threadIdx.x + half * kProducerThreads;   // 0..127
@@ -192,7 +196,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
             }
             fence_proxy_async();             // generic-proxy stores -> visible to the tensor core (async proxy)
             mbar_arrive(&a_full[s]);
+            if (P.timing) { tw += c1 - c0; tk += clock64() - c1; }
         }
+        if (P.timing && threadIdx.x == 0) { P.timing[blockIdx.x * 16 + 0] = tw; P.timing[blockIdx.x * 16 + 1] = tk; }
     } else if (warp == 2) {
         // ===== MMA issuer (one lane) =====
         if (lane == 0) {
@@ -200,14 +206,19 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
             // (A term, B term) in increasing magnitude: hl, lh, mm, hm, mh, hh   (0 = h, 1 = m, 2 = l)
             const int ta[6] = {0, 2, 1, 0, 1, 0}, tb[6] = {2, 0, 1, 1, 0, 0};
             uint32_t it = 0, g = 0;
+            long long twa = 0, twt = 0, tis = 0;
             for (uint64_t rb = blockIdx.x; rb < n_rb; rb += gridDim.x, it++) {
                 const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                const long long c0 = P.timing ? clock64() : 0;
                 mbar_wait(&a_full[s], ph);
+                if (P.timing) twa += clock64() - c0;
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(sA + s * kAStageBytes);
                 for (uint32_t t = 0; t < n_tiles; t++, g++) {
                     const uint32_t buf = g & 1, pht = (g >> 1) & 1;
+                    const long long c1 = P.timing ? clock64() : 0;
                     mbar_wait(&t_empty[buf], pht ^ 1);
+                    const long long c2 = P.timing ? clock64() : 0;
                     tc_fence_after();
                     const uint32_t d = tmem_base + buf * NT;
 #pragma unroll
@@ -217,9 +228,11 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
                         umma_bf16(d, da, db, idesc, q > 0 ? 1u : 0u);
                     }
                     umma_commit(&t_full[buf]);          // accumulator ready (implies fence::before_thread_sync)
+                    if (P.timing) { twt += c2 - c1; tis += clock64() - c2; }
                 }
                 umma_commit(&a_empty[s]);               // operand stage free once every MMA above has read it
             }
+            if (P.timing) { P.timing[blockIdx.x * 16 + 2] = twa; P.timing[blockIdx.x * 16 + 3] = twt; P.timing[blockIdx.x * 16 + 4] = tis; }
         }
         __syncwarp();
     } else if (warp >= 4) {
@@ -227,6 +240,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
         const uint32_t q = warp & 3;                    // TMEM lane quarter this warp may access
         const uint32_t lane_base = (q * 32) << 16;
         uint32_t it = 0, g = 0;
+        long long twf = 0, tld = 0, trs = 0;
         const float *nrows = P.node_rows_in_smem ? sN : P.fnode_c;   // generic pointer: shared or global
         for (uint64_t rb = blockIdx.x; rb < n_rb; rb += gridDim.x, it++) {
             float best = -INFINITY;
@@ -241,7 +255,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
             }
             for (uint32_t t = 0; t < n_tiles; t++, g++) {
                 const uint32_t buf = g & 1, pht = (g >> 1) & 1;
+                const long long c0 = P.timing ? clock64() : 0;
                 mbar_wait(&t_full[buf], pht);
+                const long long c1 = P.timing ? clock64() : 0;
                 tc_fence_after();
                 // double-buffered TMEM reads: the loads of stage s+1 are in flight while stage s is reduced
                 constexpr int kStagesPerTile = NT / (32 * LDW);
@@ -275,7 +291,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
                 }
                 tc_fence_before();
                 mbar_arrive(&t_empty[buf]);
+                if (P.timing) { twf += c1 - c0; tld += clock64() - c1; }
             }
+            const long long c2 = P.timing ? clock64() : 0;
             // resolve: the 8 candidates of the winning group, re-evaluated in fp32 with the CUDA-core kernel's fmaf order
             if (row < P.n) {
                 float bc = 0.f; uint32_t bp = kNone;
@@ -299,7 +317,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
                 if (P.out_cost) P.out_cost[row] = bc;
                 if (P.counters && nid != kNone) atomicAdd(&P.counters[nid], 1u);
             }
+            if (P.timing) trs += clock64() - c2;
         }
+        if (P.timing && threadIdx.x == 128) { P.timing[blockIdx.x * 16 + 5] = twf; P.timing[blockIdx.x * 16 + 6] = tld; P.timing[blockIdx.x * 16 + 7] = trs; }
     }
 
     // ---- teardown -------------------------------------------------------------------------------------------
@@ -315,6 +335,10 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
 
 #define RIO_COUNT_LAUNCH(L) do { if ((L).launch_counter) ++*(L).launch_counter; } while (0)
 
+// development hook (tools/umma_timing.py): device buffer of 16 u64 per CTA that receives per-role cycle counters
+static unsigned long long *g_umma_timing = nullptr;
+void affinity_umma_set_timing_buffer(unsigned long long *d) { g_umma_timing = d; }
+
 // Largest padded live-node count whose operands fit in shared memory beside the A stages.
 uint32_t affinity_umma_max_nodes() { return ((227u * 1024u - kBarBytes - kStages * kAStageBytes) / 96u) / 256u * 256u; }
 
@@ -328,7 +352,7 @@ bool launch_assign_affinity_umma(const Launch &L, const float *d_fobj, uint64_t 
     size_t smem = kBarBytes + (size_t)3 * m_pad * 32 + (size_t)kStages * kAStageBytes;
     const bool rows_in_smem = smem + (size_t)m_pad * 64 <= 227u * 1024u;
     if (rows_in_smem) smem += (size_t)m_pad * 64;
-    UmmaParams P{d_fobj, n, d_fnode_c, d_nidx_map, n_live, m_pad, d_out_idx, d_out_cost, d_counters, kRows * 16u, 128u, m_pad * 16u, 128u, rows_in_smem ? 1u : 0u};
+    UmmaParams P{d_fobj, n, d_fnode_c, d_nidx_map, n_live, m_pad, d_out_idx, d_out_cost, d_counters, kRows * 16u, 128u, m_pad * 16u, 128u, rows_in_smem ? 1u : 0u, g_umma_timing};
     const uint64_t n_rb = (n + kRows - 1) / kRows;
     const int grid = (int)(n_rb < (uint64_t)L.sm_count ? n_rb : (uint64_t)L.sm_count);
     const char *e = getenv("RIO_UMMA_LDW");   // x32 TMEM loads per double-buffer stage (A/B runs): 1 or 2 (default)
