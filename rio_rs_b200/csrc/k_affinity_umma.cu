@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
     unsigned char *sB = smem + kBarBytes;                          // 3 blocks of m_pad*32 bytes
     const uint32_t b_block_bytes = P.m_pad * 32;
     unsigned char *sA = sB + 3 * b_block_bytes;                    // kStages stages of 3 blocks
-    float *sN = reinterpret_cast<float *>(sA + kStages * kAStageBytes);   // m_pad x 16 fp32 (only when node_rows_in_smem)
+    float4 *sN4 = reinterpret_cast<float4 *>(sA + kStages * kAStageBytes);   // [4][m_pad] float4: fp32 node rows, k-chunk major (only when node_rows_in_smem)
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t n_tiles = P.m_pad / NT;
@@ -161,7 +161,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
         store_row_split(sB, b_block_bytes, P.m_pad * 16, p, f);
         if (P.node_rows_in_smem) {
 #pragma unroll
-            for (int q = 0; q < 4; q++) reinterpret_cast<float4 *>(sN + (size_t)p * 16)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+            for (int q = 0; q < 4; q++) sN4[(size_t)q * P.m_pad + p] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);   // transposed: lanes that read
+                                                                                                                     // different nodes spread over the banks
         }
     }
     fence_proxy_async();
@@ -241,7 +242,6 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
         const uint32_t lane_base = (q * 32) << 16;
         uint32_t it = 0, g = 0;
         long long twf = 0, tld = 0, trs = 0;
-        const float *nrows = P.node_rows_in_smem ? sN : P.fnode_c;   // generic pointer: shared or global
         for (uint64_t rb = blockIdx.x; rb < n_rb; rb += gridDim.x, it++) {
             float best = -INFINITY;
             uint32_t bgroup = 0;
@@ -301,11 +301,11 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
                 for (uint32_t cnd = 0; cnd < 8; cnd++) {
                     const uint32_t p = bgroup * 8 + cnd;
                     if (p >= P.n_live) break;
-                    const float4 *nr = reinterpret_cast<const float4 *>(nrows + (size_t)p * 16);
                     float acc = 0.f;
 #pragma unroll
                     for (int w = 0; w < 4; w++) {
-                        const float4 x = nr[w];
+                        const float4 x = P.node_rows_in_smem ? sN4[(size_t)w * P.m_pad + p]
+                                                             : __ldg(reinterpret_cast<const float4 *>(P.fnode_c + (size_t)p * 16) + w);
                         acc = fmaf(fo[4 * w + 0], x.x, acc); acc = fmaf(fo[4 * w + 1], x.y, acc);
                         acc = fmaf(fo[4 * w + 2], x.z, acc); acc = fmaf(fo[4 * w + 3], x.w, acc);
                     }
