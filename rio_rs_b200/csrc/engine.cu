@@ -352,7 +352,7 @@ void run_affinity(rio_placement *h, const float *d_fobj, uint64_t n, uint32_t *d
     const bool want_umma = !(v && v[0] == 'f');
     if (!h->aff_live && h->K == 16 && h->tabs.tab.n_live == 0) { launch_fill_u32(h->L(), d_out_idx, n, kNone); return; }
     if (want_umma && h->K == 16 && h->aff_live && h->aff_pad <= affinity_umma_max_nodes()) {
-        if (launch_assign_affinity_umma(h->L(), d_fobj, n, h->d_fnode_c.as<float>(), h->d_nidx_map.as<uint32_t>(), h->aff_live, h->aff_pad, d_out_idx, d_out_cost,
+        if (launch_assign_affinity_umma(h->L(), d_fobj, n, h->d_fnode_c.as<float>(), h->d_nidx_map.as<uint32_t>(), h->aff_live, h->aff_pad, h->tabs.tab.n_total, d_out_idx, d_out_cost,
                                         d_counters))
             return;
     }

@@ -14,8 +14,10 @@
 //                          tcgen05.commit -> tmem_full (and -> a_empty after the last tile of the row block)
 //   warp  3    idle (keeps the epilogue on warps 4-7, whose warp%4 selects the TMEM lane quarter they may read)
 //   warps 4-7  epilogue  : double-buffered tcgen05.ld (64 columns per stage), 3-input max over groups of 8 columns, keep
-//                          (best value, best group); arrive tmem_empty; after the last tile re-evaluate the 8 candidates of the
-//                          winning group in fp32 (same fmaf order as the CUDA-core kernel): index + exact cost.
+//                          (best value, best group); arrive tmem_empty; after the last tile emit the winning group.
+// k_affinity_resolve (second pass, CUDA cores) re-evaluates the 8 candidates of each winning group in fp32 (same fmaf order
+// as the CUDA-core kernel): node index + exact cost + per-node histogram.  It is a separate kernel because any LDS/LDG issued
+// while the tensor core streams K=16 operands out of shared memory crawls (profiles/r01_umma_role_cycles_*.txt).
 // Node operands (3 bf16 blocks, 96 B per node) stay resident in shared memory for the whole kernel.
 #include "kernels.cuh"
 #include "spec.cuh"
@@ -122,7 +124,6 @@ struct UmmaParams {
     float *out_cost;          // nullable
     uint32_t *counters;       // nullable
     uint32_t lbo_a, sbo_a, lbo_b, sbo_b;   // descriptor strides in bytes
-    uint32_t node_rows_in_smem;            // 1: fp32 node rows are also staged in shared memory for the resolve step
     unsigned long long *timing;            // optional per-CTA cycle counters (16 per CTA) for tools/umma_timing.py; NULL in production
 };
 
@@ -137,7 +138,6 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
     unsigned char *sB = smem + kBarBytes;                          // 3 blocks of m_pad*32 bytes
     const uint32_t b_block_bytes = P.m_pad * 32;
     unsigned char *sA = sB + 3 * b_block_bytes;                    // kStages stages of 3 blocks
-    float4 *sN4 = reinterpret_cast<float4 *>(sA + kStages * kAStageBytes);   // [4][m_pad] float4: fp32 node rows, k-chunk major (only when node_rows_in_smem)
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t n_tiles = P.m_pad / NT;
@@ -159,11 +159,6 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
 #pragma unroll
         for (int q = 0; q < 4; q++) { const float4 v = __ldg(row + q); f[4 * q] = v.x; f[4 * q + 1] = v.y; f[4 * q + 2] = v.z; f[4 * q + 3] = v.w; }
         store_row_split(sB, b_block_bytes, P.m_pad * 16, p, f);
-        if (P.node_rows_in_smem) {
-#pragma unroll
-            for (int q = 0; q < 4; q++) sN4[(size_t)q * P.m_pad + p] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);   // transposed: lanes that read
-                                                                                                                     // different nodes spread over the banks
-        }
     }
     fence_proxy_async();
     tc_fence_before();
@@ -245,14 +240,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
         for (uint64_t rb = blockIdx.x; rb < n_rb; rb += gridDim.x, it++) {
             float best = -INFINITY;
             uint32_t bgroup = 0;
-            // this thread's own object row, requested now so that its latency hides behind the tile loop
             const uint64_t row = rb * kRows + q * 32 + lane;
-            float fo[16];
-            {
-                const float4 *src = reinterpret_cast<const float4 *>(P.fobj + (row < P.n ? row : 0) * 16);
-#pragma unroll
-                for (int w = 0; w < 4; w++) { const float4 x = __ldg(src + w); fo[4 * w] = x.x; fo[4 * w + 1] = x.y; fo[4 * w + 2] = x.z; fo[4 * w + 3] = x.w; }
-            }
             for (uint32_t t = 0; t < n_tiles; t++, g++) {
                 const uint32_t buf = g & 1, pht = (g >> 1) & 1;
                 const long long c0 = P.timing ? clock64() : 0;
@@ -294,29 +282,11 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
                 if (P.timing) { twf += c1 - c0; tld += clock64() - c1; }
             }
             const long long c2 = P.timing ? clock64() : 0;
-            // resolve: the 8 candidates of the winning group, re-evaluated in fp32 with the CUDA-core kernel's fmaf order
-            if (row < P.n) {
-                float bc = 0.f; uint32_t bp = kNone;
-#pragma unroll 2
-                for (uint32_t cnd = 0; cnd < 8; cnd++) {
-                    const uint32_t p = bgroup * 8 + cnd;
-                    if (p >= P.n_live) break;
-                    float acc = 0.f;
-#pragma unroll
-                    for (int w = 0; w < 4; w++) {
-                        const float4 x = P.node_rows_in_smem ? sN4[(size_t)w * P.m_pad + p]
-                                                             : __ldg(reinterpret_cast<const float4 *>(P.fnode_c + (size_t)p * 16) + w);
-                        acc = fmaf(fo[4 * w + 0], x.x, acc); acc = fmaf(fo[4 * w + 1], x.y, acc);
-                        acc = fmaf(fo[4 * w + 2], x.z, acc); acc = fmaf(fo[4 * w + 3], x.w, acc);
-                    }
-                    const float cst = -acc;
-                    if (bp == kNone || cst < bc) { bc = cst; bp = p; }
-                }
-                const uint32_t nid = bp == kNone ? kNone : __ldg(P.nidx_map + bp);
-                P.out_idx[row] = nid;
-                if (P.out_cost) P.out_cost[row] = bc;
-                if (P.counters && nid != kNone) atomicAdd(&P.counters[nid], 1u);
-            }
+            // The candidate re-evaluation is NOT done here: while the tensor core streams its K=16 operands out of shared
+            // memory the L1/shared datapath is saturated and every LDS/LDG of an epilogue warp takes hundreds of cycles
+            // (profiles/r01_umma_role_cycles_*.txt: 5-7k cycles per row block).  Only the winning group of 8 columns leaves
+            // this kernel; k_affinity_resolve turns it into (node index, exact fp32 cost) in a second pass.
+            if (row < P.n) P.out_idx[row] = bgroup;
             if (P.timing) trs += clock64() - c2;
         }
         if (P.timing && threadIdx.x == 128) { P.timing[blockIdx.x * 16 + 5] = twf; P.timing[blockIdx.x * 16 + 6] = tld; P.timing[blockIdx.x * 16 + 7] = trs; }
@@ -328,6 +298,51 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * NT)) : "memory");
+    }
+}
+
+// Second pass: the 8 candidates of each object's winning group, re-evaluated in fp32 with the CUDA-core kernel's fmaf order.
+// in/out: idx[row] holds the group on entry, the interned node index on exit.  Node rows (64 KB at M = 1024) sit in L1/L2.
+__global__ void __launch_bounds__(256)
+k_affinity_resolve(const float *__restrict__ fobj, uint64_t n, const float *__restrict__ fnode_c, const uint32_t *__restrict__ nidx_map, uint32_t n_live,
+                   uint32_t *__restrict__ idx, float *__restrict__ out_cost, uint32_t *__restrict__ counters, uint32_t hist_bins) {
+    extern __shared__ uint32_t shist[];
+    for (uint32_t j = threadIdx.x; j < hist_bins; j += blockDim.x) shist[j] = 0;
+    __syncthreads();
+    for (uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (uint64_t)gridDim.x * blockDim.x) {
+        float fo[16];
+        const float4 *src = reinterpret_cast<const float4 *>(fobj + row * 16);
+#pragma unroll
+        for (int w = 0; w < 4; w++) { const float4 x = __ldg(src + w); fo[4 * w] = x.x; fo[4 * w + 1] = x.y; fo[4 * w + 2] = x.z; fo[4 * w + 3] = x.w; }
+        const uint32_t g = idx[row];
+        float bc = 0.f; uint32_t bp = kNone;
+#pragma unroll 4
+        for (uint32_t cnd = 0; cnd < 8; cnd++) {
+            const uint32_t p = g * 8 + cnd;
+            if (p >= n_live) break;
+            const float4 *nr = reinterpret_cast<const float4 *>(fnode_c + (size_t)p * 16);
+            float acc = 0.f;
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                const float4 x = __ldg(nr + w);
+                acc = fmaf(fo[4 * w + 0], x.x, acc); acc = fmaf(fo[4 * w + 1], x.y, acc);
+                acc = fmaf(fo[4 * w + 2], x.z, acc); acc = fmaf(fo[4 * w + 3], x.w, acc);
+            }
+            const float cst = -acc;
+            if (bp == kNone || cst < bc) { bc = cst; bp = p; }
+        }
+        const uint32_t nid = bp == kNone ? kNone : __ldg(nidx_map + bp);
+        idx[row] = nid;
+        if (out_cost) out_cost[row] = bc;
+        if (nid != kNone) {
+            if (hist_bins) atomicAdd(&shist[nid], 1u);
+            else if (counters) atomicAdd(&counters[nid], 1u);
+        }
+    }
+    if (hist_bins) {
+        __syncthreads();
+        if (counters)
+            for (uint32_t j = threadIdx.x; j < hist_bins; j += blockDim.x) { const uint32_t v = shist[j]; if (v) atomicAdd(&counters[j], v); }
     }
 }
 
@@ -343,16 +358,14 @@ void affinity_umma_set_timing_buffer(unsigned long long *d) { g_umma_timing = d;
 uint32_t affinity_umma_max_nodes() { return ((227u * 1024u - kBarBytes - kStages * kAStageBytes) / 96u) / 256u * 256u; }
 
 bool launch_assign_affinity_umma(const Launch &L, const float *d_fobj, uint64_t n, const float *d_fnode_c, const uint32_t *d_nidx_map, uint32_t n_live,
-                                 uint32_t m_pad, uint32_t *d_out_idx, float *d_out_cost, uint32_t *d_counters) {
+                                 uint32_t m_pad, uint32_t n_total, uint32_t *d_out_idx, float *d_out_cost, uint32_t *d_counters) {
     if (!n || !n_live) return false;
     const bool small = m_pad <= 64;
     if ((!small && (m_pad % 256)) || m_pad > affinity_umma_max_nodes()) return false;
     // K-major interleaved operands: LBO = distance between the two 16-byte K chunks, SBO = distance between 8-row groups
     // (confirmed on hardware: profiles/r01_umma_first_light.txt)
-    size_t smem = kBarBytes + (size_t)3 * m_pad * 32 + (size_t)kStages * kAStageBytes;
-    const bool rows_in_smem = smem + (size_t)m_pad * 64 <= 227u * 1024u;
-    if (rows_in_smem) smem += (size_t)m_pad * 64;
-    UmmaParams P{d_fobj, n, d_fnode_c, d_nidx_map, n_live, m_pad, d_out_idx, d_out_cost, d_counters, kRows * 16u, 128u, m_pad * 16u, 128u, rows_in_smem ? 1u : 0u, g_umma_timing};
+    const size_t smem = kBarBytes + (size_t)3 * m_pad * 32 + (size_t)kStages * kAStageBytes;
+    UmmaParams P{d_fobj, n, d_fnode_c, d_nidx_map, n_live, m_pad, d_out_idx, d_out_cost, d_counters, kRows * 16u, 128u, m_pad * 16u, 128u, g_umma_timing};
     const uint64_t n_rb = (n + kRows - 1) / kRows;
     const int grid = (int)(n_rb < (uint64_t)L.sm_count ? n_rb : (uint64_t)L.sm_count);
     const char *e = getenv("RIO_UMMA_LDW");   // x32 TMEM loads per double-buffer stage (A/B runs): 1 or 2 (default)
@@ -368,6 +381,13 @@ bool launch_assign_affinity_umma(const Launch &L, const float *d_fobj, uint64_t 
         k_affinity_umma<256, 2><<<grid, kUmmaThreads, smem, L.stream>>>(P);
     }
     RIO_COUNT_LAUNCH(L);
+    {
+        const uint32_t bins = (d_counters && n_total <= 8192) ? n_total : 0;
+        const uint64_t blocks = (n + 255) / 256, cap = (uint64_t)L.sm_count * 8;
+        k_affinity_resolve<<<(int)(blocks < cap ? blocks : cap), 256, (size_t)bins * 4, L.stream>>>(d_fobj, n, d_fnode_c, d_nidx_map, n_live, d_out_idx, d_out_cost, d_counters,
+                                                                                          bins);
+        RIO_COUNT_LAUNCH(L);
+    }
     return true;
 }
 
