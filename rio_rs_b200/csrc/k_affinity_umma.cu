@@ -7,14 +7,15 @@
 // (hh, hm, mh, mm, hl, lh; the dropped terms are <= 2^-24 relative), each term ONE tcgen05.mma (M=128 objects x
 // N=NT nodes x K=16) accumulating in fp32 in TMEM.  Nothing is materialised in HBM: the N x M grid lives only in TMEM.
 //
-// Warp roles (256 threads, one CTA per SM, persistent over 128-object row blocks):
+// Warp roles (384 threads, one CTA per SM, persistent over 128-object row blocks):
 //   warps 0-1  producers : load 128 object rows (fp32, two per thread), split to bf16 h/m/l, store the three K-major
 //                          16-byte-interleaved operand blocks into shared memory, fence.proxy.async, arrive a_full
 //   warp  2    MMA issuer: one lane issues 6 tcgen05.mma per node tile into one of two TMEM accumulators,
 //                          tcgen05.commit -> tmem_full (and -> a_empty after the last tile of the row block)
-//   warp  3    idle (keeps the epilogue on warps 4-7, whose warp%4 selects the TMEM lane quarter they may read)
-//   warps 4-7  epilogue  : double-buffered tcgen05.ld (64 columns per stage), 3-input max over groups of 8 columns, keep
-//                          (best value, best group); arrive tmem_empty; after the last tile emit the winning group.
+//   warp  3    idle (keeps the epilogue on warps 4-11, whose warp%4 selects the TMEM lane quarter they may read)
+//   warps 4-11 epilogue  : two warps per lane quarter, each owning half of every tile's columns: tcgen05.ld (64 columns
+//                          per wait), 3-input max over groups of 8 columns, running (best value, best group); arrive
+//                          tmem_empty; after the last tile the halves merge through shared memory and emit the winning group.
 // k_affinity_resolve (second pass, CUDA cores) re-evaluates the 8 candidates of each winning group in fp32 (same fmaf order
 // as the CUDA-core kernel): node index + exact cost + per-node histogram.  It is a separate kernel because any LDS/LDG issued
 // while the tensor core streams K=16 operands out of shared memory crawls (profiles/r01_umma_role_cycles_*.txt).
@@ -29,13 +30,13 @@ namespace rio {
 
 namespace {
 
-constexpr int kUmmaThreads = 256;   // 8 warps: a 9th warp would cap registers at 168/thread (3 warps on one SMSP)
+constexpr int kUmmaThreads = 384;   // 12 warps = 3 per SMSP: 170 registers per thread
 constexpr int kProducerThreads = 64;  // warps 0-1, two object rows per thread
 constexpr int kRows = 128;          // objects per row block == UMMA M
 constexpr int kStages = 2;          // A-operand stages
 constexpr uint32_t kABlockBytes = kRows * 32;            // one bf16 term of a row block: [2 k-chunks][128 rows][16 B]
 constexpr uint32_t kAStageBytes = 3 * kABlockBytes;      // h, m, l
-constexpr uint32_t kBarBytes = 128;
+constexpr uint32_t kBarBytes = 128 + 2 * 128 * 8;   // mbarriers + TMEM slot, then two (best value, best group) merge slots of 128 rows
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -135,18 +136,20 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
     uint64_t *t_full = a_empty + kStages;                          // [2]
     uint64_t *t_empty = t_full + 2;                                // [2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 2);
+    float2 *sMerge = reinterpret_cast<float2 *>(smem + 128);          // [2][128]: (best value, best group bits) handed from column half B to half A
     unsigned char *sB = smem + kBarBytes;                          // 3 blocks of m_pad*32 bytes
     const uint32_t b_block_bytes = P.m_pad * 32;
     unsigned char *sA = sB + 3 * b_block_bytes;                    // kStages stages of 3 blocks
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long t_begin = P.timing ? clock64() : 0;
     const uint32_t n_tiles = P.m_pad / NT;
     const uint64_t n_rb = (P.n + kRows - 1) / kRows;
 
     // ---- one-time setup: barriers, TMEM, node operands ----------------------------------------------------------
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; s++) { mbar_init(&a_full[s], kProducerThreads); mbar_init(&a_empty[s], 1); }
-        for (int b = 0; b < 2; b++) { mbar_init(&t_full[b], 1); mbar_init(&t_empty[b], 128); }
+        for (int b = 0; b < 2; b++) { mbar_init(&t_full[b], 1); mbar_init(&t_empty[b], 256); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -165,6 +168,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const long long t_setup = P.timing ? clock64() : 0;
 
     if (warp < 2) {
         // ===== producers: object rows -> bf16 h/m/l operand blocks (two rows per thread) =====
@@ -232,38 +236,40 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
         }
         __syncwarp();
     } else if (warp >= 4) {
-        // ===== epilogue warps 4..7: TMEM -> registers -> running (best value, best group of 8 columns) =====
+        // ===== epilogue warps 4..11: TMEM -> registers -> running (best value, best group of 8 columns) =====
+        // A warp's tcgen05.ld occupies its own issue slot until the data has landed (measured: load time and reduce time
+        // ADD within one warp, profiles/r01_umma_epilogue_experiments.txt), so two warps share every TMEM lane quarter:
+        // warps 4-7 ("half A") own the lower NT/2 columns of each tile, warps 8-11 ("half B") the upper NT/2, and while one
+        // loads the other reduces on the same SM sub-partition.  Half B hands its (best, group) to half A through shared memory.
         const uint32_t q = warp & 3;                    // TMEM lane quarter this warp may access
+        const uint32_t half = (warp - 4) >> 2;          // 0 = columns [0, NT/2), 1 = columns [NT/2, NT)
         const uint32_t lane_base = (q * 32) << 16;
+        constexpr int kChunks = NT / 64;                // 32-column chunks per half tile
+        constexpr int kBatch = kChunks < LDW ? kChunks : LDW;
         uint32_t it = 0, g = 0;
         long long twf = 0, tld = 0, trs = 0;
         for (uint64_t rb = blockIdx.x; rb < n_rb; rb += gridDim.x, it++) {
             float best = -INFINITY;
             uint32_t bgroup = 0;
-            const uint64_t row = rb * kRows + q * 32 + lane;
+            const uint32_t r = q * 32 + lane;           // row inside the row block == TMEM lane
+            const uint64_t row = rb * kRows + r;
             for (uint32_t t = 0; t < n_tiles; t++, g++) {
                 const uint32_t buf = g & 1, pht = (g >> 1) & 1;
                 const long long c0 = P.timing ? clock64() : 0;
                 mbar_wait(&t_full[buf], pht);
                 const long long c1 = P.timing ? clock64() : 0;
                 tc_fence_after();
-                // double-buffered TMEM reads: the loads of stage s+1 are in flight while stage s is reduced
-                constexpr int kStagesPerTile = NT / (32 * LDW);
-                uint32_t v[2][LDW][32];
-                const uint32_t tcol = tmem_base + lane_base + buf * NT;
+                const uint32_t tcol = tmem_base + lane_base + buf * NT + half * (NT / 2);
 #pragma unroll
-                for (int w = 0; w < LDW; w++) tmem_ld32(tcol + w * 32, v[0][w]);
-                tmem_wait_ld();
+                for (int c0i = 0; c0i < kChunks; c0i += kBatch) {
+                    uint32_t v[kBatch][32];
 #pragma unroll
-                for (int st = 0; st < kStagesPerTile; st++) {
-                    if (st + 1 < kStagesPerTile) {
+                    for (int w = 0; w < kBatch; w++) tmem_ld32(tcol + (c0i + w) * 32, v[w]);
+                    tmem_wait_ld();
 #pragma unroll
-                        for (int w = 0; w < LDW; w++) tmem_ld32(tcol + ((st + 1) * LDW + w) * 32, v[(st + 1) & 1][w]);
-                    }
-#pragma unroll
-                    for (int w = 0; w < LDW; w++) {
-                        uint32_t (&x)[32] = v[st & 1][w];
-                        const uint32_t col0 = t * NT + (st * LDW + w) * 32;
+                    for (int w = 0; w < kBatch; w++) {
+                        uint32_t (&x)[32] = v[w];
+                        const uint32_t col0 = t * NT + half * (NT / 2) + (c0i + w) * 32;
                         if (col0 + 32 > P.n_live) {          // warp-uniform: only the padded tail of the last tile
 #pragma unroll
                             for (int i = 0; i < 32; i++) if (col0 + i >= P.n_live) x[i] = 0xFF800000u;   // -inf
@@ -275,18 +281,27 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
                             if (gm > best) { best = gm; bgroup = (col0 >> 3) + gq; }
                         }
                     }
-                    if (st + 1 < kStagesPerTile) tmem_wait_ld();
                 }
                 tc_fence_before();
                 mbar_arrive(&t_empty[buf]);
                 if (P.timing) { twf += c1 - c0; tld += clock64() - c1; }
             }
             const long long c2 = P.timing ? clock64() : 0;
-            // The candidate re-evaluation is NOT done here: while the tensor core streams its K=16 operands out of shared
-            // memory the L1/shared datapath is saturated and every LDS/LDG of an epilogue warp takes hundreds of cycles
-            // (profiles/r01_umma_role_cycles_*.txt: 5-7k cycles per row block).  Only the winning group of 8 columns leaves
-            // this kernel; k_affinity_resolve turns it into (node index, exact fp32 cost) in a second pass.
-            if (row < P.n) P.out_idx[row] = bgroup;
+            // merge the two column halves: within a tile half A's columns precede half B's, and both walk the tiles in
+            // order, so on equal values the smaller group index is the earlier column
+            float2 *slot = sMerge + (it & 1) * kRows;
+            if (half == 1) slot[r] = make_float2(best, __uint_as_float(bgroup));
+            asm volatile("bar.sync 1, 256;" ::: "memory");     // the 8 epilogue warps only
+            if (half == 0) {
+                const float2 o = slot[r];
+                const uint32_t og = __float_as_uint(o.y);
+                if (o.x > best || (o.x == best && og < bgroup)) bgroup = og;
+                // The candidate re-evaluation is NOT done here: while the tensor core streams its K=16 operands out of shared
+                // memory the L1/shared datapath is saturated and every LDS/LDG of an epilogue warp takes hundreds of cycles
+                // (profiles/r01_umma_role_cycles_*.txt).  Only the winning group of 8 columns leaves this kernel;
+                // k_affinity_resolve turns it into (node index, exact fp32 cost) in a second pass.
+                if (row < P.n) P.out_idx[row] = bgroup;
+            }
             if (P.timing) trs += clock64() - c2;
         }
         if (P.timing && threadIdx.x == 128) { P.timing[blockIdx.x * 16 + 5] = twf; P.timing[blockIdx.x * 16 + 6] = tld; P.timing[blockIdx.x * 16 + 7] = trs; }
@@ -295,6 +310,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
     // ---- teardown -------------------------------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
+    if (P.timing && threadIdx.x == 0) { P.timing[blockIdx.x * 16 + 8] = t_setup - t_begin; P.timing[blockIdx.x * 16 + 9] = clock64() - t_begin; P.timing[blockIdx.x * 16 + 10] = t_begin; }
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * NT)) : "memory");

@@ -10,6 +10,7 @@ import rio_rs_b200 as R
 from oracle import pyoracle as O
 
 N, M = 10_000_000, 1024
+
 p = R.GpuObjectPlacement(device=0)
 addrs, _, _ = O.synth_nodes(M)
 p.set_nodes(addrs, None, np.random.default_rng(13).uniform(-1, 1, (M, 16)).astype(np.float32))
@@ -33,9 +34,11 @@ p._ck(p.L.rio_cuda_memcpy_d2h(p.h, out.ctypes.data_as(C.c_void_p), buf, out.nbyt
 p.sync()
 L.rio_dev_umma_timing(p.h, None)
 t = out.reshape(148, 16).astype(np.float64)
-names = ["producer wait a_empty", "producer work", "mma wait a_full", "mma wait t_empty", "mma issue+commit", "epi wait t_full", "epi ld+reduce", "epi resolve"]
+names = ["producer wait a_empty", "producer work", "mma wait a_full", "mma wait t_empty", "mma issue+commit", "epi wait t_full", "epi ld+reduce", "epi resolve", "setup (B operands, TMEM)", "CTA total"]
 rb_per_cta = (N / 128) / 148
 print("kernel %.3f ms (with timing hooks); per CTA: %.0f row blocks, %.0f tiles; kernel cycles ~%.0f" % (ms, rb_per_cta, rb_per_cta * 4, ms * 1e-3 * 1.965e9))
 for k, nm in enumerate(names):
     per = t[:, k].mean()
-    print("  %-24s %12.0f cycles/CTA  %8.1f per row block  %7.1f per tile" % (nm, per, per / rb_per_cta, per / (rb_per_cta * 4)))
+    print("  %-24s %12.0f cycles/CTA (min %10.0f max %10.0f)  %8.1f per row block  %7.1f per tile" % (nm, per, t[:, k].min(), t[:, k].max(), per / rb_per_cta, per / (rb_per_cta * 4)))
+starts = t[:, 10] - t[:, 10].min()
+print("  CTA start skew: max %.0f cycles; clock64 rate check: CTA total mean %.0f cycles vs %.3f ms -> %.3f GHz" % (starts.max(), t[:, 9].mean(), ms, t[:, 9].mean() / (ms * 1e-3) / 1e9))
