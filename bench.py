@@ -64,20 +64,88 @@ def measured_peaks():
     return HBM_FALLBACK_GBS, "fallback"
 
 
+def measured_tensor_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            if "bf16_tflops" in d:
+                return float(d["bf16_tflops"]), "measured"
+        except Exception:
+            pass
+    return 1590.0, "fallback"
+
+
+def extra_configs(p, O, n, seeds_unused):
+    """The other single-GPU configs of BASELINE.json, measured with the same event discipline (N = 1 only):
+    C2 = 1 M x 64 weighted rendezvous; C3 = 10 M x 1024, 16-dim affinity cost + argmin on the tensor cores."""
+    import rio_rs_b200 as R
+
+    out = {}
+    q = R.GpuObjectPlacement(device=p.device_info()["device"])
+    addrs, _, w = O.synth_nodes(64)
+    q.set_nodes(addrs, w)
+    s = q.new_set(1 << 20)
+    s.synth_keys(0, 1 << 20, 1)
+    for _ in range(5):
+        s.assign()
+    q.sync()
+    q.event_record(0)
+    for _ in range(50):
+        s.assign()
+    q.event_record(1)
+    q.sync()
+    ms = q.event_elapsed_ms(0, 1) / 50
+    out["C2_rendezvous_1Mx64"] = {"ms": ms, "placements_per_s": (1 << 20) / (ms * 1e-3), "note": "resident keys, weights 1..16"}
+    del s
+    M, K = 1024, 16
+    addrs, _, _ = O.synth_nodes(M)
+    fn = np.random.default_rng(13).uniform(-1, 1, (M, K)).astype(np.float32)
+    q.set_nodes(addrs, None, fn)
+    s = q.new_set(n)
+    s.load_keys(np.arange(n, dtype=np.uint64))
+    fo = np.random.default_rng(11).uniform(-1, 1, (n, K)).astype(np.float32)
+    s.load_feats(fo)
+    for _ in range(3):
+        s.assign(True)
+    q.sync()
+    q.event_record(0)
+    for _ in range(10):
+        s.assign(True)
+    q.event_record(1)
+    q.sync()
+    ms = q.event_elapsed_ms(0, 1) / 10
+    # parity spot-check of the tensor-core path against the fp64 oracle (checker only)
+    got = s.read(0, 20000)
+    idx, cost, gap = O.assign_affinity(fo[:20000], fn, np.ones(M, dtype=np.uint32), threads=8)
+    ok = bool(((got == idx) | (gap <= 1e-5 * np.abs(cost) + 1e-12)).all())
+    peak, src = measured_tensor_peak()
+    issued = 6 * 2 * K * M * n / (ms * 1e-3) / 1e12  # six bf16 cross-term MMAs per (object, node) pair
+    out["C3_affinity_10Mx1024xK16"] = {
+        "ms": ms, "placements_per_s": n / (ms * 1e-3), "kernels": "k_affinity_umma (tcgen05/TMEM, bf16x3 split) + k_affinity_resolve",
+        "parity_vs_fp64_oracle_20k": ok,
+        "roofline": {"bound": "tensor", "achieved": issued, "peak": peak, "unit": "TFLOP/s", "frac": issued / peak, "peak_source": src,
+                     "note": "bf16 FLOP/s actually issued (6 cross terms); algorithmic 2KM FLOP/s = achieved / 6"},
+    }
+    return out
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
 
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, gpu_index):
-        self.idx = gpu_index
+    def __init__(self, gpu_indices):
+        self.idx = ",".join(str(i) for i in gpu_indices)
         self.proc = None
         self.lines = []
 
     def start(self):
+        if os.environ.get("RIO_BENCH_NO_SMI"):
+            return
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", self.idx, "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -88,10 +156,14 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
+    def mark(self):
+        """Samples collected before this call (warm-up) are dropped."""
+        self.lines = []
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.25)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -159,13 +231,14 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--objects", type=int, default=N_OBJECTS, help="objects per rank (default: the BASELINE size)")
     ap.add_argument("--nodes", type=int, default=N_NODES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C2/C3 side measurements (N = 1 only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -232,11 +305,18 @@ def main():
     def step(i):
         return sets[i % N_SETS].assign_bounded(n_global, 5, 4, 4)
 
+    # ONE sampler for the whole job (rank 0 watches every GPU of the run): a poller per rank contends for the driver
+    # and showed up as ~0.4 ms per step at N = 8 (profiles/r01_scale_n8.json vs r01_scale_n8_one_sampler.json)
+    clocks = ClockSampler(range(world)) if rank == 0 else None
+    if clocks:
+        clocks.start()
     for i in range(args.warmup):
         passes = step(i)
     barrier_sync()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
+    if clocks:
+        time.sleep(0.3)   # make sure the sampler is producing before the timed region starts
+        clocks.mark()
+    barrier_sync()
     l0 = p.launch_count()
     p.event_record(0)
     for i in range(args.steps):
@@ -245,7 +325,6 @@ def main():
     barrier_sync()
     ms_total = max_over_ranks(p.event_elapsed_ms(0, 1))
     launches = p.launch_count() - l0
-    clk = clocks.stop()
     ms_per_step = ms_total / args.steps
     value = n_global / (ms_per_step * 1e-3)
 
@@ -258,6 +337,13 @@ def main():
         sets[i % N_SETS].assign()
     p.event_record(3)
     p.sync()
+    if clocks and len(clocks.lines) < 3 * world:   # short runs: keep the same kernel running until a few samples exist
+        t_end = time.perf_counter() + 0.6
+        while time.perf_counter() < t_end:
+            for i in range(10):
+                sets[i % N_SETS].assign()
+            p.sync()
+    clk = clocks.stop() if clocks else None   # covers the timed steps, the kernel-only loop (and the burst above, if any)
     kern_ms = p.event_elapsed_ms(2, 3) / args.steps
     peak, peak_src = measured_peaks()
     traffic, traffic_src = ncu_traffic() if (n == N_OBJECTS and M == N_NODES) else (None, None)
@@ -304,6 +390,13 @@ def main():
         cpu = {"value": m / dt, "unit": "placements/s", "cores": cores, "kind": "port",
                "sample": "first %d of the 10M objects x %d nodes, oracle/rio_oracle.c orc_assign_hrw, %d threads, %.1f s" % (m, M, cores, dt)}
 
+    extra = None
+    if rank == 0 and world == 1 and n == N_OBJECTS and not args.no_extra:
+        try:
+            extra = extra_configs(p, O, n, seeds)
+        except Exception as e:  # the headline line must still be printed
+            extra = {"error": repr(e)}
+
     if rank == 0:
         line = {
             "metric": "placements/sec", "value": value, "unit": "placements/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -321,6 +414,7 @@ def main():
             "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": clk,
+            "extra_configs": extra,
         }
         print(json.dumps(line), flush=True)
     if dist:

@@ -133,9 +133,10 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *a_full = reinterpret_cast<uint64_t *>(smem);         // [kStages]
     uint64_t *a_empty = a_full + kStages;                          // [kStages]
-    uint64_t *t_full = a_empty + kStages;                          // [2]
-    uint64_t *t_empty = t_full + 2;                                // [2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 2);
+    constexpr uint32_t NBUF = (NT == 128) ? 4 : 2;                  // TMEM accumulator buffers of NT columns each
+    uint64_t *t_full = a_empty + kStages;                          // [NBUF]
+    uint64_t *t_empty = t_full + 4;                                // [NBUF]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 4);
     float2 *sMerge = reinterpret_cast<float2 *>(smem + 128);          // [2][128]: (best value, best group bits) handed from column half B to half A
     unsigned char *sB = smem + kBarBytes;                          // 3 blocks of m_pad*32 bytes
     const uint32_t b_block_bytes = P.m_pad * 32;
@@ -149,11 +150,11 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
     // ---- one-time setup: barriers, TMEM, node operands ----------------------------------------------------------
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; s++) { mbar_init(&a_full[s], kProducerThreads); mbar_init(&a_empty[s], 1); }
-        for (int b = 0; b < 2; b++) { mbar_init(&t_full[b], 1); mbar_init(&t_empty[b], 256); }
+        for (uint32_t b = 0; b < NBUF; b++) { mbar_init(&t_full[b], 1); mbar_init(&t_empty[b], 256); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * NT)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(NBUF * NT)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     for (uint32_t p = threadIdx.x; p < P.m_pad; p += blockDim.x) {
@@ -176,24 +177,26 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
         long long tw = 0, tk = 0;
         for (uint64_t rb = blockIdx.x; rb < n_rb; rb += gridDim.x, it++) {
             const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+            // request this row block's object rows BEFORE waiting for the stage: the DRAM latency hides behind the wait
+            float f[2][16];
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                const uint64_t row = rb * kRows + threadIdx.x + half * kProducerThreads;
+                if (row < P.n) {
+                    const float4 *src = reinterpret_cast<const float4 *>(P.fobj + row * 16);
+#pragma unroll
+                    for (int q = 0; q < 4; q++) { const float4 v = __ldg(src + q); f[half][4 * q] = v.x; f[half][4 * q + 1] = v.y; f[half][4 * q + 2] = v.z; f[half][4 * q + 3] = v.w; }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 16; k++) f[half][k] = 0.f;
+                }
+            }
             const long long c0 = P.timing ? clock64() : 0;
             mbar_wait(&a_empty[s], ph ^ 1);
             const long long c1 = P.timing ? clock64() : 0;
 #pragma unroll
-            for (int half = 0; half < 2; half++) {
-                const uint32_t r = threadIdx.x + half * kProducerThreads;   // 0..127
-                const uint64_t row = rb * kRows + r;
-                float f[16];
-                if (row < P.n) {
-                    const float4 *src = reinterpret_cast<const float4 *>(P.fobj + row * 16);
-#pragma unroll
-                    for (int q = 0; q < 4; q++) { const float4 v = __ldg(src + q); f[4 * q] = v.x; f[4 * q + 1] = v.y; f[4 * q + 2] = v.z; f[4 * q + 3] = v.w; }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 16; k++) f[k] = 0.f;
-                }
-                store_row_split(sA + s * kAStageBytes, kABlockBytes, kRows * 16, r, f);
-            }
+            for (int half = 0; half < 2; half++)
+                store_row_split(sA + s * kAStageBytes, kABlockBytes, kRows * 16, threadIdx.x + half * kProducerThreads, f[half]);
             fence_proxy_async();             // generic-proxy stores -> visible to the tensor core (async proxy)
             mbar_arrive(&a_full[s]);
             if (P.timing) { tw += c1 - c0; tk += clock64() - c1; }
@@ -215,7 +218,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(sA + s * kAStageBytes);
                 for (uint32_t t = 0; t < n_tiles; t++, g++) {
-                    const uint32_t buf = g & 1, pht = (g >> 1) & 1;
+                    const uint32_t buf = g % NBUF, pht = (g / NBUF) & 1;
                     const long long c1 = P.timing ? clock64() : 0;
                     mbar_wait(&t_empty[buf], pht ^ 1);
                     const long long c2 = P.timing ? clock64() : 0;
@@ -254,7 +257,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
             const uint32_t r = q * 32 + lane;           // row inside the row block == TMEM lane
             const uint64_t row = rb * kRows + r;
             for (uint32_t t = 0; t < n_tiles; t++, g++) {
-                const uint32_t buf = g & 1, pht = (g >> 1) & 1;
+                const uint32_t buf = g % NBUF, pht = (g / NBUF) & 1;
                 const long long c0 = P.timing ? clock64() : 0;
                 mbar_wait(&t_full[buf], pht);
                 const long long c1 = P.timing ? clock64() : 0;
@@ -313,7 +316,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
     if (P.timing && threadIdx.x == 0) { P.timing[blockIdx.x * 16 + 8] = t_setup - t_begin; P.timing[blockIdx.x * 16 + 9] = clock64() - t_begin; P.timing[blockIdx.x * 16 + 10] = t_begin; }
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * NT)) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(NBUF * NT)) : "memory");
     }
 }
 
@@ -392,7 +395,10 @@ bool launch_assign_affinity_umma(const Launch &L, const float *d_fobj, uint64_t 
     } else if (ldw == 1) {
         cudaFuncSetAttribute(k_affinity_umma<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k_affinity_umma<256, 1><<<grid, kUmmaThreads, smem, L.stream>>>(P);
-    } else {   // (4 per stage needs 256 staging registers and spills: not compiled)
+    } else if (getenv("RIO_UMMA_NT") && atoi(getenv("RIO_UMMA_NT")) == 128) {   // A/B: four 128-column accumulators
+        cudaFuncSetAttribute(k_affinity_umma<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_affinity_umma<128, 2><<<grid, kUmmaThreads, smem, L.stream>>>(P);
+    } else {
         cudaFuncSetAttribute(k_affinity_umma<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k_affinity_umma<256, 2><<<grid, kUmmaThreads, smem, L.stream>>>(P);
     }
