@@ -370,7 +370,9 @@ uint32_t capacity_of(uint64_t n_total, uint32_t w, uint64_t w_sum, uint32_t num,
 void assign_host_pipelined(rio_placement *h, const uint64_t *keys, const float *feats, size_t n, uint32_t *out) {
     ensure_tab(h);
     if (feats) REQUIRE(h->K > 0, "assign with object features needs node features (set_nodes feats)");
-    const size_t chunk = 1u << 20;
+    // chunks of two full kernel waves (about 0.9 M objects on 148 SMs): whole waves leave no tail, small chunks keep the
+    // pipeline fill/drain (first H2D, last D2H) short
+    const size_t chunk = feats ? (size_t)(1u << 20) : (size_t)(2 * assign_wave_objects(h->sm_count));
     h->s_keys.ensure(n * 8, h->stream);
     h->s_idx.ensure(n * 4, h->stream);
     if (feats) h->s_feats.ensure(n * (size_t)h->K * 4, h->stream);

@@ -446,6 +446,10 @@ static int assign_variant() {
 
 #define RIO_COUNT_LAUNCH(L) do { if ((L).launch_counter) ++*(L).launch_counter; } while (0)
 
+// Objects one full wave of the default rendezvous launch covers (persistent CTAs x objects per tile): host code that
+// pipelines chunks sizes them in whole waves so that no chunk ends on a partially filled wave.
+uint64_t assign_wave_objects(int sm_count) { return (uint64_t)sm_count * 3 * kAssignThreads * 4; }
+
 void launch_assign_hrw(const Launch &L, const uint64_t *d_keys, uint64_t n, const NodeTabDev &tab, uint32_t *d_out_idx,
                        uint32_t *d_counters, const uint32_t *d_sel, uint64_t n_sel) {
     const uint64_t n_work = d_sel ? n_sel : n;

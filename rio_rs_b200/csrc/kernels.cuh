@@ -47,6 +47,7 @@ struct Launch { cudaStream_t stream; int sm_count; uint64_t *launch_counter; };
 // solver
 void launch_assign_hrw(const Launch &L, const uint64_t *d_keys, uint64_t n, const NodeTabDev &tab, uint32_t *d_out_idx,
                        uint32_t *d_counters /*nullable, n_total entries*/, const uint32_t *d_sel /*nullable*/, uint64_t n_sel);
+uint64_t assign_wave_objects(int sm_count);
 void launch_assign_affinity(const Launch &L, const float *d_fobj, uint64_t n, const float *d_fnode /*n_total x K*/,
                             const uint32_t *d_live /*n_total flags*/, uint32_t n_total, uint32_t K, uint32_t *d_out_idx,
                             float *d_out_cost /*nullable*/, uint32_t *d_counters);
