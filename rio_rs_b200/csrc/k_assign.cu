@@ -352,8 +352,10 @@ k_mix_rate(uint32_t iters, uint32_t *sink) {
     for (int k = 0; k < 4; k++) {   // opaque per-object constants (read from memory so the compiler cannot relate them)
         b[k] = sink[8 + ((threadIdx.x * 8 + k) & 255)] | 1u; ab[k] = sink[8 + ((threadIdx.x * 8 + 4 + k) & 255)]; gm[k] = 0;
     }
-    uint32_t s0a = blockIdx.x * 0x9E3779B9u + 12345u, s0b = s0a ^ 0x7F4A7C15u;
-    const uint32_t s1a = 0x6478BD64u ^ s0a, s1b = 0xA0B428DBu ^ s0b, s2a = 0xA0761D64u + s0a, s2b = 0xE7037ED1u + s0b;
+    // per-thread (not warp-uniform) node constants, so that the xor stays ONE 3-input LOP3 like in the real loop
+    uint32_t s0a = sink[8 + ((threadIdx.x + 64) & 255)] + blockIdx.x, s0b = s0a ^ 0x7F4A7C15u;
+    const uint32_t s1a = sink[8 + ((threadIdx.x + 1) & 255)], s1b = sink[8 + ((threadIdx.x + 2) & 255)];   // opaque, per thread
+    const uint32_t s2a = sink[8 + ((threadIdx.x + 3) & 255)], s2b = sink[8 + ((threadIdx.x + 4) & 255)];
     for (uint32_t it = 0; it < iters; it++) {
 #pragma unroll
         for (int r = 0; r < 8; r++) {

@@ -101,6 +101,49 @@ impl GpuObjectPlacement {
     }
 }
 
+/// Micro-batching front end (rio_cuda_resolver_*): a blocking per-id call with the signature of
+/// `Service::get_or_create_placement` (service.rs:193-197); concurrent callers are coalesced into one `place_batch`.
+pub struct Resolver {
+    raw: *mut sys::rio_resolver,
+    _engine: Arc<Engine>, // keeps the engine alive for as long as the resolver exists
+}
+unsafe impl Send for Resolver {}
+unsafe impl Sync for Resolver {}
+impl Drop for Resolver {
+    fn drop(&mut self) {
+        unsafe { sys::rio_cuda_resolver_destroy(self.raw) }
+    }
+}
+impl GpuObjectPlacement {
+    /// `self_idx = Some(i)`: the reference's rule (claim for the serving node, service.rs:244-252); `None`: rendezvous solver.
+    pub fn resolver(&self, self_idx: Option<u32>, max_batch: u32, max_wait_us: u32) -> Result<Resolver, ObjectPlacementError> {
+        let (policy, me) = match self_idx { Some(i) => (sys::RIO_PLACE_SELF, i), None => (sys::RIO_PLACE_HRW, 0) };
+        let mut raw = ptr::null_mut();
+        check(self.h(), unsafe { sys::rio_cuda_resolver_create(self.h(), policy, me, max_batch, max_wait_us, &mut raw) })?;
+        Ok(Resolver { raw, _engine: self.engine.clone() })
+    }
+}
+impl Resolver {
+    /// Blocking; call it from `spawn_blocking` or a dedicated thread.
+    pub fn get_or_create_placement(&self, handler_type: &str, handler_id: &str) -> Result<Option<String>, ObjectPlacementError> {
+        let mut buf = vec![0u8; 256];
+        let mut len: libc::size_t = 0;
+        let st = unsafe {
+            sys::rio_cuda_resolver_resolve_str(self.raw, handler_type.as_ptr() as *const _, handler_type.len(), handler_id.as_ptr() as *const _,
+                                               handler_id.len(), buf.as_mut_ptr() as *mut _, buf.len(), &mut len)
+        };
+        if st != sys::RIO_OK {
+            let msg = unsafe { CStr::from_ptr(sys::rio_cuda_resolver_last_error()).to_string_lossy().into_owned() };
+            return Err(if st == sys::RIO_ERR_UPSTREAM { ObjectPlacementError::Upstream(msg) } else { ObjectPlacementError::Unknown(msg) });
+        }
+        if len == usize::MAX {
+            return Ok(None);
+        }
+        buf.truncate(len.min(256));
+        Ok(Some(String::from_utf8_lossy(&buf).into_owned()))
+    }
+}
+
 /// FFI calls block for tens of microseconds: keep them off the async workers (SURVEY section 7 hard part 5).
 async fn blocking<T: Send + 'static>(f: impl FnOnce() -> Result<T, ObjectPlacementError> + Send + 'static) -> Result<T, ObjectPlacementError> {
     tokio::task::spawn_blocking(f).await.map_err(|e| ObjectPlacementError::Unknown(e.to_string()))?
