@@ -158,6 +158,12 @@ rio_status  rio_cuda_set_commit(rio_objset *s);
 #define RIO_COMM_ID_BYTES 128
 rio_status  rio_cuda_comm_unique_id(uint8_t out_id[RIO_COMM_ID_BYTES]);       /* rank 0; ship to the others */
 rio_status  rio_cuda_comm_init(rio_placement *h, int32_t rank, int32_t world, const uint8_t id[RIO_COMM_ID_BYTES]);
+/* Peer-memory variant of the exchange (preferred on one NVLink/NVSwitch box): every rank exports a small window, the host
+ * gathers the world handles (any bootstrap) and attaches them; from then on the counter exchange is ONE kernel that stores
+ * into the peers' windows over NVLink and spins on flags -- no NCCL launch on the critical path.  At most 16 ranks. */
+#define RIO_IPC_HANDLE_BYTES 64
+rio_status  rio_cuda_comm_ipc_export(rio_placement *h, int32_t world, uint32_t max_nodes, uint8_t out_handle[RIO_IPC_HANDLE_BYTES]);
+rio_status  rio_cuda_comm_ipc_attach(rio_placement *h, int32_t rank, int32_t world, const uint8_t *handles /* world x RIO_IPC_HANDLE_BYTES */);
 rio_status  rio_cuda_comm_info(rio_placement *h, int32_t *rank, int32_t *world);
 /* all-gather + sum of an M-entry u32 counter vector (host in/out); exposed for tests and host-side logic */
 rio_status  rio_cuda_comm_sum_counters(rio_placement *h, uint32_t *inout, uint32_t M);

@@ -71,6 +71,8 @@ SIGNATURES = {
     "rio_cuda_set_commit": (C.c_int32, [H]),
     "rio_cuda_comm_unique_id": (C.c_int32, [vp]),
     "rio_cuda_comm_init": (C.c_int32, [H, C.c_int32, C.c_int32, vp]),
+    "rio_cuda_comm_ipc_export": (C.c_int32, [H, C.c_int32, C.c_uint32, vp]),
+    "rio_cuda_comm_ipc_attach": (C.c_int32, [H, C.c_int32, C.c_int32, vp]),
     "rio_cuda_comm_info": (C.c_int32, [H, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "rio_cuda_comm_sum_counters": (C.c_int32, [H, vp, C.c_uint32]),
     "rio_cuda_dev_alloc": (C.c_int32, [H, sz, C.POINTER(vp)]),

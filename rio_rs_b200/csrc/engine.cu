@@ -149,6 +149,11 @@ struct rio_placement {
 
     NcclComm comm = nullptr;
     int rank = 0, world = 1;
+    // peer-memory exchange window (CUDA IPC): slots[2][world][xchg_nodes] + flags[world]
+    uint32_t *xchg_mine = nullptr;
+    uint32_t *xchg_peer[16] = {};
+    uint32_t xchg_nodes = 0, xchg_epoch = 0;
+    bool xchg_ready = false;
 
     Launch L() { return Launch{stream, sm_count, &launches}; }
     uint32_t *d_error() { return reinterpret_cast<uint32_t *>(d_scalars + S_COUNT); }
@@ -336,6 +341,11 @@ void dir_upsert_dev(rio_placement *h, const uint64_t *d_keys, const uint32_t *d_
 
 // ---- counter exchange: the single collective of the path (all-gather of M u32 per rank, then a sum) -------------
 void exchange_counters(rio_placement *h, const uint32_t *d_local, uint32_t *d_global, uint32_t M) {
+    if (h->world > 1 && h->xchg_ready && M <= h->xchg_nodes) {
+        // one kernel: P2P stores into every peer's window + flags over NVLink, no NCCL launch on the critical path
+        launch_exchange_p2p(h->L(), d_local, h->xchg_peer, (uint32_t)h->rank, (uint32_t)h->world, M, h->xchg_nodes, ++h->xchg_epoch, d_global);
+        return;
+    }
     if (h->world <= 1 || !h->comm) {
         if (d_local != d_global) CUDA_TRY(cudaMemcpyAsync(d_global, d_local, (size_t)M * 4, cudaMemcpyDeviceToDevice, h->stream));
         return;
@@ -503,6 +513,11 @@ void rio_cuda_destroy(rio_placement *h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    if (h->xchg_mine) {
+        for (int p = 0; p < h->world && p < 16; p++)
+            if (h->xchg_ready && p != h->rank && h->xchg_peer[p]) cudaIpcCloseMemHandle(h->xchg_peer[p]);
+        cudaFree(h->xchg_mine);
+    }
     DevBuf *bufs[] = {&h->tabs.recs, &h->tabs.classes, &h->tabs.by_idx, &h->tabs_masked.recs, &h->tabs_masked.classes, &h->tabs_masked.by_idx,
                       &h->d_node_state, &h->d_live, &h->d_fnode, &h->d_fnode_c, &h->d_nidx_map, &h->s_keys, &h->s_idx, &h->s_idx2, &h->s_sel, &h->s_slots, &h->s_keys2, &h->s_feats,
                       &h->s_packed, &h->s_offsets, &h->s_cost, &h->s_misc, &h->s_flush, &h->s_gather};
@@ -1057,6 +1072,42 @@ rio_status rio_cuda_comm_init(rio_placement *h, int32_t rank, int32_t world, con
         memcpy(nid.internal, id, RIO_COMM_ID_BYTES);
         NCCL_TRY(g_nccl.CommInitRank(&h->comm, world, nid, rank));
         h->rank = rank; h->world = world;
+    });
+}
+
+/* Peer-memory exchange: export this rank's window, then attach every rank's handle (gathered by the host bootstrap). */
+rio_status rio_cuda_comm_ipc_export(rio_placement *h, int32_t world, uint32_t max_nodes, uint8_t out_handle[RIO_IPC_HANDLE_BYTES]) {
+    if (!h || !out_handle) { g_last_error = "null argument"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] {
+        REQUIRE(world >= 1 && world <= 16 && max_nodes > 0, "bad world / max_nodes (at most 16 ranks)");
+        static_assert(sizeof(cudaIpcMemHandle_t) <= RIO_IPC_HANDLE_BYTES, "IPC handle does not fit");
+        if (h->xchg_mine) { CUDA_TRY(cudaStreamSynchronize(h->stream)); CUDA_TRY(cudaFree(h->xchg_mine)); h->xchg_mine = nullptr; h->xchg_ready = false; }
+        const size_t words = (size_t)2 * world * max_nodes + world;
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&h->xchg_mine), words * 4));   // cudaMalloc (not the async pool): IPC needs a plain allocation
+        CUDA_TRY(cudaMemset(h->xchg_mine, 0, words * 4));
+        h->xchg_nodes = max_nodes;
+        h->xchg_epoch = 0;
+        cudaIpcMemHandle_t hd;
+        CUDA_TRY(cudaIpcGetMemHandle(&hd, h->xchg_mine));
+        memset(out_handle, 0, RIO_IPC_HANDLE_BYTES);
+        memcpy(out_handle, &hd, sizeof hd);
+    });
+}
+
+rio_status rio_cuda_comm_ipc_attach(rio_placement *h, int32_t rank, int32_t world, const uint8_t *handles) {
+    if (!h || !handles) { g_last_error = "null argument"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] {
+        REQUIRE(world >= 1 && world <= 16 && rank >= 0 && rank < world && h->xchg_mine, "export the window first / bad rank");
+        for (int p = 0; p < world; p++) {
+            if (p == rank) { h->xchg_peer[p] = h->xchg_mine; continue; }
+            cudaIpcMemHandle_t hd;
+            memcpy(&hd, handles + (size_t)p * RIO_IPC_HANDLE_BYTES, sizeof hd);
+            void *ptr = nullptr;
+            CUDA_TRY(cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+            h->xchg_peer[p] = reinterpret_cast<uint32_t *>(ptr);
+        }
+        h->rank = rank; h->world = world;
+        h->xchg_ready = true;
     });
 }
 

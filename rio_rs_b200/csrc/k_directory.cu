@@ -395,7 +395,51 @@ __global__ void k_gather_keys(const uint64_t *__restrict__ keys, const uint32_t 
     }
 }
 
+// ---- the counter exchange as ONE kernel over NVLink peer memory -------------------------------------
+// Every rank owns a window {slots[2][world][max_nodes] u32, flags[world] u32} that all peers have mapped through CUDA
+// IPC.  push: my M counters go into slot [epoch&1][rank] of every peer's window (plain P2P stores over NVLink);
+// signal: a release store of the epoch into flags[rank] of every peer; wait: spin (acquire loads, system scope) until my
+// own window carries this epoch from every rank; sum.  Slots are double buffered by epoch parity: nobody can be two
+// exchanges ahead, because every exchange needs everybody's flag.
+struct XchgPeers { uint32_t *win[16]; };
+__global__ void __launch_bounds__(1024)
+k_exchange_p2p(const uint32_t *__restrict__ local, XchgPeers peers, uint32_t rank, uint32_t world, uint32_t M, uint32_t max_nodes, uint32_t epoch,
+               uint32_t *__restrict__ out_global) {
+    const size_t slot_words = (size_t)2 * world * max_nodes;
+    const size_t par = (size_t)(epoch & 1u) * world * max_nodes;
+    for (uint32_t p = 0; p < world; p++) {
+        uint32_t *dst = peers.win[p] + par + (size_t)rank * max_nodes;
+        for (uint32_t j = threadIdx.x; j < M; j += blockDim.x) dst[j] = local[j];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < world) {
+        uint32_t *flag = peers.win[threadIdx.x] + slot_words + rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+    }
+    if (threadIdx.x < world) {
+        const uint32_t *mine = peers.win[rank] + slot_words + threadIdx.x;
+        uint32_t v;
+        do { asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory"); } while ((int32_t)(v - epoch) < 0);
+    }
+    __syncthreads();
+    const uint32_t *src = peers.win[rank] + par;
+    for (uint32_t j = threadIdx.x; j < M; j += blockDim.x) {
+        uint32_t s = 0;
+        for (uint32_t r = 0; r < world; r++) s += src[(size_t)r * max_nodes + j];
+        out_global[j] = s;
+    }
+}
+
 }  // namespace
+
+void launch_exchange_p2p(const Launch &L, const uint32_t *d_local, uint32_t *const *peer_windows, uint32_t rank, uint32_t world, uint32_t M, uint32_t max_nodes,
+                         uint32_t epoch, uint32_t *d_out_global) {
+    XchgPeers P{};
+    for (uint32_t p = 0; p < world && p < 16; p++) P.win[p] = peer_windows[p];
+    k_exchange_p2p<<<1, 1024, 0, L.stream>>>(d_local, P, rank, world, M, max_nodes, epoch, d_out_global);
+    RIO_COUNT_LAUNCH(L);
+}
 
 void launch_dir_init(const Launch &L, DirSlot *slots, uint64_t cap) {
     k_dir_init<<<grid_for(cap, 256, L.sm_count, 8), 256, 0, L.stream>>>(slots, cap);

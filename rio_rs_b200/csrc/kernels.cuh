@@ -92,6 +92,8 @@ void launch_classify(const Launch &L, const uint32_t *d_cur, uint64_t n, const u
 void launch_scatter_const(const Launch &L, uint32_t *d_out, const uint32_t *d_sel, uint64_t n_sel, uint32_t v);
 void launch_gather_keys(const Launch &L, const uint64_t *d_keys, const uint32_t *d_sel, uint64_t n_sel, uint64_t *d_out_keys, const uint32_t *d_idx,
                         uint32_t *d_out_idx);
+void launch_exchange_p2p(const Launch &L, const uint32_t *d_local, uint32_t *const *peer_windows, uint32_t rank, uint32_t world, uint32_t M, uint32_t max_nodes,
+                         uint32_t epoch, uint32_t *d_out_global);
 void launch_sum_gathered(const Launch &L, const uint32_t *d_gathered, uint32_t world, uint32_t M, uint32_t *d_out);
 void launch_l2_flush(const Launch &L, uint32_t *d_buf, uint64_t n_words, uint32_t v);
 

@@ -279,6 +279,15 @@ class GpuObjectPlacement:
         buf = np.frombuffer(bytes(unique_id), dtype=np.uint8).copy()
         self._ck(self.L.rio_cuda_comm_init(self.h, rank, world, _ptr(buf)))
 
+    def comm_ipc_export(self, world, max_nodes=8192):
+        buf = np.zeros(64, dtype=np.uint8)
+        self._ck(self.L.rio_cuda_comm_ipc_export(self.h, world, max_nodes, _ptr(buf)))
+        return buf.tobytes()
+
+    def comm_ipc_attach(self, rank, world, handles):
+        buf = np.frombuffer(b"".join(handles), dtype=np.uint8).copy()
+        self._ck(self.L.rio_cuda_comm_ipc_attach(self.h, rank, world, _ptr(buf)))
+
     def comm_sum_counters(self, counters):
         c = np.ascontiguousarray(counters, dtype=np.uint32).copy()
         self._ck(self.L.rio_cuda_comm_sum_counters(self.h, _ptr(c), len(c)))

@@ -82,6 +82,8 @@ extern "C" {
 
     pub fn rio_cuda_comm_unique_id(out_id: *mut u8) -> rio_status;
     pub fn rio_cuda_comm_init(h: *mut rio_placement, rank: i32, world: i32, id: *const u8) -> rio_status;
+    pub fn rio_cuda_comm_ipc_export(h: *mut rio_placement, world: i32, max_nodes: u32, out_handle: *mut u8) -> rio_status;
+    pub fn rio_cuda_comm_ipc_attach(h: *mut rio_placement, rank: i32, world: i32, handles: *const u8) -> rio_status;
     pub fn rio_cuda_comm_info(h: *mut rio_placement, rank: *mut i32, world: *mut i32) -> rio_status;
     pub fn rio_cuda_comm_sum_counters(h: *mut rio_placement, inout: *mut u32, m: u32) -> rio_status;
 
