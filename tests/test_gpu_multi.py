@@ -11,8 +11,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, n, M, q):
+def _worker(rank, world, port, n, M, q, comm):
     sys.path.insert(0, ROOT)
+    os.environ["RIO_COMM"] = comm   # "p2p": CUDA-IPC windows over NVLink (default), "nccl": ncclAllGather
     import torch.distributed as dist
 
     import rio_rs_b200 as R
@@ -45,7 +46,8 @@ def _worker(rank, world, port, n, M, q):
     dist.destroy_process_group()
 
 
-def test_two_gpu_sharded_results_equal_single_process_oracle(oracle):
+@pytest.mark.parametrize("comm", ["p2p", "nccl"])
+def test_two_gpu_sharded_results_equal_single_process_oracle(oracle, comm):
     import torch
     import torch.multiprocessing as mp
 
@@ -57,8 +59,8 @@ def test_two_gpu_sharded_results_equal_single_process_oracle(oracle):
     n, M, world = 400_000, 48, 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + os.getpid() % 1000
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, M, q)) for r in range(world)]
+    port = 29600 + os.getpid() % 1000 + (7 if comm == "nccl" else 0)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, M, q, comm)) for r in range(world)]
     for pr in procs:
         pr.start()
     res = sorted(q.get(timeout=600) for _ in range(world))
