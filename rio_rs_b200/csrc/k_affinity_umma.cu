@@ -16,9 +16,9 @@
 //   warps 4-11 epilogue  : two warps per lane quarter, each owning half of every tile's columns: tcgen05.ld (64 columns
 //                          per wait), 3-input max over groups of 8 columns, running (best value, best group); arrive
 //                          tmem_empty; after the last tile the halves merge through shared memory and emit the winning group.
-// k_affinity_resolve (second pass, CUDA cores) re-evaluates the 8 candidates of each winning group in fp32 (same fmaf order
-// as the CUDA-core kernel): node index + exact cost + per-node histogram.  It is a separate kernel because any LDS/LDG issued
-// while the tensor core streams K=16 operands out of shared memory crawls (profiles/r01_umma_role_cycles_*.txt).
+// k_affinity_resolve (second pass, CUDA cores, one warp per object) re-evaluates the 8 candidates of each winning group in
+// fp32: node index + fp32 cost + per-node histogram.  It is a separate kernel because any LDS/LDG issued while the tensor
+// core streams K=16 operands out of shared memory crawls (profiles/r01_umma_role_cycles_*.txt).
 // Node operands (3 bf16 blocks, 96 B per node) stay resident in shared memory for the whole kernel.
 #include "kernels.cuh"
 #include "spec.cuh"
@@ -320,42 +320,62 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
     }
 }
 
-// Second pass: the 8 candidates of each object's winning group, re-evaluated in fp32 with the CUDA-core kernel's fmaf order.
-// in/out: idx[row] holds the group on entry, the interned node index on exit.  Node rows (64 KB at M = 1024) sit in L1/L2.
+// Second pass: the 8 candidates of each object's winning group, re-evaluated in fp32.  One warp per object: the 8 candidate
+// node rows are 512 contiguous bytes, so lane l = 4*r + c loads the 16-byte piece c of candidate row r (ONE coalesced
+// 128-bit load per lane, four 128-byte lines per object -- the per-thread version of this loop touched 32 scattered sectors
+// per load and was L1-wavefront bound at 1.17 ms, profiles/r01_launches_final.csv), multiplies it with piece c of the
+// object's own row, and two xor-shuffles finish the 16-term dot product; three more pick the smallest (cost, position).
+// in/out: idx[row] holds the group on entry, the interned node index on exit.
 __global__ void __launch_bounds__(256)
 k_affinity_resolve(const float *__restrict__ fobj, uint64_t n, const float *__restrict__ fnode_c, const uint32_t *__restrict__ nidx_map, uint32_t n_live,
                    uint32_t *__restrict__ idx, float *__restrict__ out_cost, uint32_t *__restrict__ counters, uint32_t hist_bins) {
     extern __shared__ uint32_t shist[];
     for (uint32_t j = threadIdx.x; j < hist_bins; j += blockDim.x) shist[j] = 0;
     __syncthreads();
-    for (uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (uint64_t)gridDim.x * blockDim.x) {
-        float fo[16];
-        const float4 *src = reinterpret_cast<const float4 *>(fobj + row * 16);
+    const uint32_t lane = threadIdx.x & 31, r = lane >> 2, c = lane & 3;
+    const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    constexpr int U = 4;   // objects in flight per warp
+    for (uint64_t base = warp0 * U; base < n; base += nwarps * U) {
+        float acc[U];
+        uint32_t pos[U];
 #pragma unroll
-        for (int w = 0; w < 4; w++) { const float4 x = __ldg(src + w); fo[4 * w] = x.x; fo[4 * w + 1] = x.y; fo[4 * w + 2] = x.z; fo[4 * w + 3] = x.w; }
-        const uint32_t g = idx[row];
-        float bc = 0.f; uint32_t bp = kNone;
-#pragma unroll 4
-        for (uint32_t cnd = 0; cnd < 8; cnd++) {
-            const uint32_t p = g * 8 + cnd;
-            if (p >= n_live) break;
-            const float4 *nr = reinterpret_cast<const float4 *>(fnode_c + (size_t)p * 16);
-            float acc = 0.f;
-#pragma unroll
-            for (int w = 0; w < 4; w++) {
-                const float4 x = __ldg(nr + w);
-                acc = fmaf(fo[4 * w + 0], x.x, acc); acc = fmaf(fo[4 * w + 1], x.y, acc);
-                acc = fmaf(fo[4 * w + 2], x.z, acc); acc = fmaf(fo[4 * w + 3], x.w, acc);
+        for (int u = 0; u < U; u++) {
+            const uint64_t row = base + u;
+            acc[u] = 0.f; pos[u] = kNone;
+            if (row < n) {
+                const uint32_t g = __ldg(idx + row);                      // same address for the whole warp
+                const uint32_t p = g * 8 + r;
+                const float4 fo = __ldg(reinterpret_cast<const float4 *>(fobj + row * 16) + c);
+                const float4 x = __ldg(reinterpret_cast<const float4 *>(fnode_c + (size_t)p * 16) + c);   // rows beyond n_live are zero padding
+                float a = fo.x * x.x;
+                a = fmaf(fo.y, x.y, a); a = fmaf(fo.z, x.z, a); a = fmaf(fo.w, x.w, a);
+                acc[u] = a;
+                pos[u] = p < n_live ? p : kNone;
             }
-            const float cst = -acc;
-            if (bp == kNone || cst < bc) { bc = cst; bp = p; }
         }
-        const uint32_t nid = bp == kNone ? kNone : __ldg(nidx_map + bp);
-        idx[row] = nid;
-        if (out_cost) out_cost[row] = bc;
-        if (nid != kNone) {
-            if (hist_bins) atomicAdd(&shist[nid], 1u);
-            else if (counters) atomicAdd(&counters[nid], 1u);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            float a = acc[u];
+            a += __shfl_xor_sync(0xFFFFFFFFu, a, 1);
+            a += __shfl_xor_sync(0xFFFFFFFFu, a, 2);                      // every lane of a row now holds the same dot product
+            float cst = pos[u] == kNone ? INFINITY : -a;
+            uint32_t p = pos[u];
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+                const float oc = __shfl_xor_sync(0xFFFFFFFFu, cst, o);
+                const uint32_t op = __shfl_xor_sync(0xFFFFFFFFu, p, o);
+                if (oc < cst || (oc == cst && op < p)) { cst = oc; p = op; }
+            }
+            const uint64_t row = base + u;
+            if (lane == 0 && row < n) {
+                const uint32_t nid = p == kNone ? kNone : __ldg(nidx_map + p);
+                idx[row] = nid;
+                if (out_cost) out_cost[row] = p == kNone ? 0.f : cst;
+                if (nid != kNone) {
+                    if (hist_bins) atomicAdd(&shist[nid], 1u);
+                    else if (counters) atomicAdd(&counters[nid], 1u);
+                }
+            }
         }
     }
     if (hist_bins) {
@@ -405,7 +425,7 @@ bool launch_assign_affinity_umma(const Launch &L, const float *d_fobj, uint64_t 
     RIO_COUNT_LAUNCH(L);
     {
         const uint32_t bins = (d_counters && n_total <= 8192) ? n_total : 0;
-        const uint64_t blocks = (n + 255) / 256, cap = (uint64_t)L.sm_count * 8;
+        const uint64_t blocks = (n + 31) / 32, cap = (uint64_t)L.sm_count * 8;   // one warp per 4 objects, 8 warps per CTA
         k_affinity_resolve<<<(int)(blocks < cap ? blocks : cap), 256, (size_t)bins * 4, L.stream>>>(d_fobj, n, d_fnode_c, d_nidx_map, n_live, d_out_idx, d_out_cost, d_counters,
                                                                                           bins);
         RIO_COUNT_LAUNCH(L);
