@@ -334,43 +334,40 @@ k_affinity_resolve(const float *__restrict__ fobj, uint64_t n, const float *__re
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31, r = lane >> 2, c = lane & 3;
     const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const float4 *fobj4 = reinterpret_cast<const float4 *>(fobj) + c;        // piece c of an object row: + 4*row
+    const float4 *fnode4 = reinterpret_cast<const float4 *>(fnode_c) + lane;  // piece c of candidate r of group g: + 32*g
     constexpr int U = 4;   // objects in flight per warp
     for (uint64_t base = warp0 * U; base < n; base += nwarps * U) {
         float acc[U];
-        uint32_t pos[U];
+        uint32_t grp[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            const uint64_t row = base + u;
-            acc[u] = 0.f; pos[u] = kNone;
-            if (row < n) {
-                const uint32_t g = __ldg(idx + row);                      // same address for the whole warp
-                const uint32_t p = g * 8 + r;
-                const float4 fo = __ldg(reinterpret_cast<const float4 *>(fobj + row * 16) + c);
-                const float4 x = __ldg(reinterpret_cast<const float4 *>(fnode_c + (size_t)p * 16) + c);   // rows beyond n_live are zero padding
-                float a = fo.x * x.x;
-                a = fmaf(fo.y, x.y, a); a = fmaf(fo.z, x.z, a); a = fmaf(fo.w, x.w, a);
-                acc[u] = a;
-                pos[u] = p < n_live ? p : kNone;
-            }
+            const uint64_t row = base + u < n ? base + u : n - 1;               // clamp: the tail recomputes the last object
+            grp[u] = __ldg(idx + row);                                          // one address for the whole warp
+            const float4 fo = __ldg(fobj4 + row * 4);
+            const float4 x = __ldg(fnode4 + (size_t)grp[u] * 32);              // rows beyond n_live are zero padding
+            float a = fo.x * x.x;
+            a = fmaf(fo.y, x.y, a); a = fmaf(fo.z, x.z, a); a = fmaf(fo.w, x.w, a);
+            acc[u] = a;
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
             float a = acc[u];
             a += __shfl_xor_sync(0xFFFFFFFFu, a, 1);
-            a += __shfl_xor_sync(0xFFFFFFFFu, a, 2);                      // every lane of a row now holds the same dot product
-            float cst = pos[u] == kNone ? INFINITY : -a;
-            uint32_t p = pos[u];
-#pragma unroll
-            for (int o = 4; o < 32; o <<= 1) {
-                const float oc = __shfl_xor_sync(0xFFFFFFFFu, cst, o);
-                const uint32_t op = __shfl_xor_sync(0xFFFFFFFFu, p, o);
-                if (oc < cst || (oc == cst && op < p)) { cst = oc; p = op; }
-            }
-            const uint64_t row = base + u;
-            if (lane == 0 && row < n) {
-                const uint32_t nid = p == kNone ? kNone : __ldg(nidx_map + p);
-                idx[row] = nid;
-                if (out_cost) out_cost[row] = p == kNone ? 0.f : cst;
+            a += __shfl_xor_sync(0xFFFFFFFFu, a, 2);                            // every lane of a candidate row holds its dot product
+            const uint32_t p = grp[u] * 8 + r;
+            // order-preserving integer image of cost = -dot (+inf for padding), minimum by one warp reduction;
+            // the lowest lane holding the minimum is the lowest candidate position (ties -> lowest node)
+            const uint32_t bits = p < n_live ? __float_as_uint(-a) : 0x7F800000u;
+            const int key = (int)(bits ^ ((uint32_t)((int)bits >> 31) & 0x7FFFFFFFu));
+            const int kmin = __reduce_min_sync(0xFFFFFFFFu, key);
+            const uint32_t first = __ffs(__ballot_sync(0xFFFFFFFFu, key == kmin)) - 1;
+            const uint32_t bp = __shfl_sync(0xFFFFFFFFu, p, first);
+            if (lane == first && base + u < n) {
+                const bool none = bits == 0x7F800000u && !(p < n_live);
+                const uint32_t nid = none ? kNone : __ldg(nidx_map + bp);
+                idx[base + u] = nid;
+                if (out_cost) out_cost[base + u] = none ? 0.f : -a;
                 if (nid != kNone) {
                     if (hist_bins) atomicAdd(&shist[nid], 1u);
                     else if (counters) atomicAdd(&counters[nid], 1u);
