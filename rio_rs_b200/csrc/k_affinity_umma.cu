@@ -350,6 +350,8 @@ k_affinity_resolve(const float *__restrict__ fobj, uint64_t n, const float *__re
             a = fmaf(fo.y, x.y, a); a = fmaf(fo.z, x.z, a); a = fmaf(fo.w, x.w, a);
             acc[u] = a;
         }
+        uint32_t my_p = kNone;      // lane u (< U) ends up owning object base+u: its winning position and cost
+        float my_c = 0.f;
 #pragma unroll
         for (int u = 0; u < U; u++) {
             float a = acc[u];
@@ -362,16 +364,18 @@ k_affinity_resolve(const float *__restrict__ fobj, uint64_t n, const float *__re
             const int key = (int)(bits ^ ((uint32_t)((int)bits >> 31) & 0x7FFFFFFFu));
             const int kmin = __reduce_min_sync(0xFFFFFFFFu, key);
             const uint32_t first = __ffs(__ballot_sync(0xFFFFFFFFu, key == kmin)) - 1;
-            const uint32_t bp = __shfl_sync(0xFFFFFFFFu, p, first);
-            if (lane == first && base + u < n) {
-                const bool none = bits == 0x7F800000u && !(p < n_live);
-                const uint32_t nid = none ? kNone : __ldg(nidx_map + bp);
-                idx[base + u] = nid;
-                if (out_cost) out_cost[base + u] = none ? 0.f : -a;
-                if (nid != kNone) {
-                    if (hist_bins) atomicAdd(&shist[nid], 1u);
-                    else if (counters) atomicAdd(&counters[nid], 1u);
-                }
+            const uint32_t bp = __shfl_sync(0xFFFFFFFFu, p < n_live ? p : kNone, first);
+            const float bc = __shfl_sync(0xFFFFFFFFu, -a, first);
+            if (lane == (uint32_t)u) { my_p = bp; my_c = bc; }
+        }
+        // lanes 0..U-1 finish one object each: four independent map lookups, one 16-byte store
+        if (lane < U && base + lane < n) {
+            const uint32_t nid = my_p == kNone ? kNone : __ldg(nidx_map + my_p);
+            idx[base + lane] = nid;
+            if (out_cost) out_cost[base + lane] = my_p == kNone ? 0.f : my_c;
+            if (nid != kNone) {
+                if (hist_bins) atomicAdd(&shist[nid], 1u);
+                else if (counters) atomicAdd(&counters[nid], 1u);
             }
         }
     }
