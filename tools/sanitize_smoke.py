@@ -1,0 +1,65 @@
+"""Small pass over every kernel of librio_cuda for compute-sanitizer (memcheck / racecheck); sizes kept tiny.
+Usage (GPU box): compute-sanitizer --tool memcheck python tools/sanitize_smoke.py [--no-umma]"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import rio_rs_b200 as R
+from oracle import pyoracle as O
+
+skip_umma = "--no-umma" in sys.argv
+p = R.GpuObjectPlacement(device=0, directory_capacity=1024)
+addrs, seeds, w = O.synth_nodes(70)
+p.set_nodes(addrs[:64], w[:64])
+keys = O.synth_keys(5000, 1)
+want = O.assign_hrw(keys, seeds[:64], w[:64])
+assert (p.assign_batch(keys) == want).all()                         # k_assign_hrw_v2 (+ chunked host pipeline)
+os.environ["RIO_ASSIGN_VARIANT"] = "1"
+assert (p.assign_batch(keys) == want).all()                         # k_assign_hrw
+os.environ.pop("RIO_ASSIGN_VARIANT")
+assert (p.place_batch(keys, "hrw") == want).all()                   # lookup, classify, assign(sel), gather, upsert (with growth + rehash)
+assert (p.lookup_many(keys) == want).all()
+ids = [("Obj", str(i)) for i in range(3000)]
+hk = p.hash_ids(ids)                                                # k_hash_ids
+assert hk[7] == O.object_key("Obj", "7")
+p.update_many(hk, np.full(len(hk), 3, dtype=np.uint32))
+assert p.clean_node(3) >= len(hk)                                   # k_dir_clean_node
+p.remove_many(hk[:100])
+p.node_set_active(5, False)
+p.place_batch(keys[:2000], "self", addrs[1])                        # clean_flagged + scatter_const path
+moved = p.rebalance("leave", 5)                                     # k_dir_rebalance_leave
+j = p.node_upsert(addrs[64], int(w[64]))
+p.rebalance("join", j)                                              # k_dir_rebalance_join
+p.load_counters(); p.directory_len()
+s = p.new_set(20000)
+s.synth_keys(0, 20000, 2)                                           # k_synth_keys
+s.assign()
+s.assign_bounded(0, 101, 100, 4)                                    # k_select_spill + masked table
+p.node_set_active(9, False)
+s.rebalance("leave", 9)                                             # k_select_on_node + assign(sel)
+j2 = p.node_upsert(addrs[65], int(w[65]))
+s.rebalance("join", j2)                                             # k_rebalance_join
+s.counters(); s.commit()
+r = R.Resolver(p, policy="hrw", max_wait_us=100)
+for k in keys[:50]:
+    r.resolve(int(k))
+r.close()
+p.bench_mix_rate(2)                                                 # k_mix_rate
+# affinity: CUDA-core kernels always, tensor-core kernel unless --no-umma
+q = R.GpuObjectPlacement(device=0)
+fn = np.random.default_rng(1).uniform(-1, 1, (300, 16)).astype(np.float32)
+fo = np.random.default_rng(2).uniform(-1, 1, (3000, 16)).astype(np.float32)
+a2, _, _ = O.synth_nodes(300)
+q.set_nodes(a2, None, fn)
+idx, cost, gap = O.assign_affinity(fo, fn, np.ones(300, dtype=np.uint32))
+for var in (["ffma"] if skip_umma else ["ffma", "umma"]):
+    os.environ["RIO_AFFINITY_VARIANT"] = var
+    got = q.assign_batch(obj_feats=fo)
+    assert ((got == idx) | (gap <= 1e-5 * np.abs(cost))).all(), var
+os.environ.pop("RIO_AFFINITY_VARIANT")
+q8 = R.GpuObjectPlacement(device=0)
+q8.set_nodes(a2[:20], None, fn[:20, :8].copy())
+q8.assign_batch(obj_feats=fo[:500, :8].copy())                       # generic-K kernel
+print("sanitize_smoke: all paths ran, results match the oracle")
