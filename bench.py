@@ -409,7 +409,7 @@ def main():
                          "kernel": "k_assign_hrw_v2", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_OBJECT * n, "peak_source": peak_src,
                          "note": "integer-ALU bound by construction (1024 pair hashes per 12 B); see alu_roofline"},
             "alu_roofline": {"bound": "int-alu", "achieved": pair_rate, "peak": mix_peak, "unit": "pair-hashes/s", "frac": pair_rate / mix_peak,
-                             "peak_source": "rio_cuda_bench_mix_rate: register-only replay of the same IMAD/SHF/LOP3/IMAD/VIMNMX3 mix, measured in this run"},
+                             "peak_source": "rio_cuda_bench_mix_rate: register-only replay of the same IMAD/IMAD/VIMNMX3 mix, measured in this run"},
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": int(launches),

@@ -114,12 +114,11 @@ static inline orc_objh obj_hash(uint64_t key) {
     orc_objh o; o.b = (uint32_t)(h >> 32) | 1u; o.ab = a * o.b; return o;
 }
 
-/* u = ((p ^ (p >> 15) ^ s1) * C1 + s2) mod 2^32 with p = (s0*b + ab) mod 2^32;
+/* spec v3: u = (p * (s1 | 1) + s2) mod 2^32 with p = (s0*b + ab) mod 2^32 -- two multiply-adds;
  * (s0, s1) = (lo32, hi32) of the node seed, s2 = lo32(mix64(seed ^ SALT_NODE2)) */
 static inline uint32_t pair_u(orc_objh o, uint64_t seed, uint32_t s2) {
     uint32_t p = (uint32_t)seed * o.b + o.ab;
-    uint32_t q = p ^ (p >> 15) ^ (uint32_t)(seed >> 32);
-    return q * PAIR_C1 + s2;
+    return p * ((uint32_t)(seed >> 32) | 1u) + s2;
 }
 uint32_t orc_pair_hash(uint64_t key, uint64_t node_seed) {
     return pair_u(obj_hash(key), node_seed, (uint32_t)orc_mix64(node_seed ^ SALT_NODE2));

@@ -223,7 +223,7 @@ void build_tab(rio_placement *h, TabBufs &tb, const std::vector<uint8_t> *closed
     std::vector<ClassRec> classes;
     for (size_t q = 0; q < live.size(); q++) {
         const NodeInfo &ni = h->nodes[live[q].idx];
-        recs[q] = NodeRec{(uint32_t)ni.seed, live[q].idx, (uint32_t)(ni.seed >> 32), (uint32_t)ni.seed2};
+        recs[q] = NodeRec{(uint32_t)ni.seed, live[q].idx, (uint32_t)(ni.seed >> 32) | 1u, (uint32_t)ni.seed2};
         if (q == 0 || live[q].invw != live[q - 1].invw) classes.push_back(ClassRec{(uint32_t)q, live[q].invw});
     }
     const uint32_t n_classes = (uint32_t)classes.size();
@@ -233,7 +233,7 @@ void build_tab(rio_placement *h, TabBufs &tb, const std::vector<uint8_t> *closed
     for (uint32_t j = 0; j < n_total; j++) {
         const NodeInfo &ni = h->nodes[j];
         const bool lv = ni.live() && !(closed && (*closed)[j]);
-        by_idx[j] = make_uint4((uint32_t)ni.seed, lv ? inv_weight(ni.weight) : 0u, (uint32_t)(ni.seed >> 32), (uint32_t)ni.seed2);
+        by_idx[j] = make_uint4((uint32_t)ni.seed, lv ? inv_weight(ni.weight) : 0u, (uint32_t)(ni.seed >> 32) | 1u, (uint32_t)ni.seed2);
     }
     cudaStream_t st = h->stream;
     tb.recs.ensure(recs.size() * sizeof(NodeRec), st);

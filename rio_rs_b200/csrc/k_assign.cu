@@ -2,7 +2,7 @@
 //
 // Weighted rendezvous: one thread owns OPT objects, the block walks the class-sorted
 // node table staged in shared memory (one broadcast LDS.128 per node per warp), and per (object,node) pair
-// the integer work is  p = s0*b + ab (IMAD);  q = p ^ (p>>15) ^ s1 (SHF, LOP3);  u = q*C1 + s2 (IMAD);  max (VIMNMX3 / 2).
+// the integer work is  p = s0*b + ab (IMAD);  u = p*m + s2 (IMAD);  max (VIMNMX3 / 2)   [spec v3].
 // The -log2 and the 64-bit weighted score are evaluated once per (object, weight class), not per pair.
 // The kernel is integer-ALU bound (12 B of HBM traffic per object against M pair hashes), see DESIGN.md 5.1.
 #include "kernels.cuh"
@@ -114,29 +114,47 @@ k_assign_hrw(const uint64_t *__restrict__ keys, uint64_t n_work, NodeTabDev tab,
 
 
 // ---- v2: grouped 3-input max, index resolved afterwards -------------------------------------------------
-// Per pair only the hash (IMAD, SHF, LOP3, IMAD) and half a VIMNMX3 are issued: the running maximum of a
+// Per pair only the hash (IMAD, IMAD) and half a VIMNMX3 are issued: the running maximum of a
 // group of <= 32 consecutive nodes of one weight class is folded with __vimax3_u32, the group that raised the
 // class maximum is remembered by its start position, and the node index is recovered at the very end by
 // re-hashing the single winning group (<= 32 pairs per object, ~3 % extra at M = 1024).
+// Full groups run BLK nodes of straight-line code per loop trip (no bounds inside); the partial group that ends
+// a class runs 8-node blocks, then pairs, then a single node.  Positions are 16-bit (the launcher sends larger
+// tables to k_assign_hrw): a group is remembered as (class end << 16) | group start, one register per object.
 constexpr uint32_t kGroup = 32;
+constexpr uint32_t kV2MaxLive = 0xFFFF;
+constexpr uint32_t kV2Slack = kGroup;   // records behind the shared-memory table that the index scan may read (never matches)
 
-__device__ __forceinline__ uint32_t resolve_in_group(ObjHash o, const NodeTabDev &tab, uint32_t gs, uint32_t cend, uint32_t u_target) {
-    const uint32_t ge = min(gs + kGroup, cend);
-    const uint4 *grec = reinterpret_cast<const uint4 *>(tab.recs);
-    for (uint32_t q = gs; q < ge; q++) {
+// The scan against the table in global memory, last position first so the lowest position that reproduces
+// u_target wins: tables larger than one shared-memory chunk, and the tie path below.  Out of line: rare, and it
+// keeps registers and instruction cache for the kernel body.
+__device__ __noinline__ uint32_t resolve_in_group_global(uint32_t b, uint32_t ab, const uint4 *grec, uint32_t pk, uint32_t u_target) {
+    const ObjHash o{b, ab};
+    const uint32_t gs = pk & 0xFFFFu, cend = pk >> 16;
+    uint32_t nid = kNone;
+    for (uint32_t q = min(gs + kGroup, cend); q-- > gs;) {
         const uint4 r = __ldg(grec + q);
-        if (pair_hash(o, r.x, r.z, r.w) == u_target) return r.y;
+        if (pair_hash(o, r.x, r.z, r.w) == u_target) nid = r.y;
     }
-    return kNone;  // unreachable: the group produced u_target
+    return nid;
 }
 
-template <int OPT, int MINB>
+// Two classes with EQUAL 64-bit scores (rare: ~2^-40 per class pair): the larger u wins, and an exact (score, u)
+// tie goes to the lower node index (spec 3.4).  Out of line so the common path is two compares and a branch.
+__device__ __noinline__ bool equal_score_takes(uint32_t b, uint32_t ab, const uint4 *grec, uint32_t pk_new, uint32_t pk_old, uint32_t u_new, uint32_t u_old) {
+    if (u_new != u_old) return u_new > u_old;
+    if (pk_old == 0) return false;
+    return resolve_in_group_global(b, ab, grec, pk_new, u_new) < resolve_in_group_global(b, ab, grec, pk_old, u_old);
+}
+
+template <int OPT, int MINB, int BLK>
 __global__ void __launch_bounds__(kAssignThreads, MINB)
 k_assign_hrw_v2(const uint64_t *__restrict__ keys, uint64_t n_work, NodeTabDev tab, uint32_t *__restrict__ out_idx,
                 uint32_t *__restrict__ counters, const uint32_t *__restrict__ sel, uint32_t chunk_cap, uint32_t hist_bins) {
+    static_assert(BLK == 8 || BLK == 16 || BLK == 32, "BLK divides the group");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint4 *srec = reinterpret_cast<uint4 *>(smem_raw);
-    uint32_t *shist = reinterpret_cast<uint32_t *>(smem_raw + (size_t)chunk_cap * sizeof(uint4));
+    uint32_t *shist = reinterpret_cast<uint32_t *>(smem_raw + (size_t)(chunk_cap + kV2Slack) * sizeof(uint4));
     const uint32_t n_live = tab.n_live;
     const bool single_chunk = n_live <= chunk_cap;
     const uint4 *grec = reinterpret_cast<const uint4 *>(tab.recs);
@@ -146,23 +164,27 @@ k_assign_hrw_v2(const uint64_t *__restrict__ keys, uint64_t n_work, NodeTabDev t
         for (uint32_t j = threadIdx.x; j < n_live; j += blockDim.x) srec[j] = __ldg(grec + j);
     __syncthreads();
 
+#define RIO_FOLD_PAIR(R0, R1)                                                                                                        \
+    _Pragma("unroll") for (int k = 0; k < OPT; k++)                                                                                  \
+        gm[k] = __vimax3_u32(gm[k], pair_hash(ObjHash{b[k], ab[k]}, (R0).x, (R0).z, (R0).w), pair_hash(ObjHash{b[k], ab[k]}, (R1).x, (R1).z, (R1).w))
+#define RIO_GROUP_DONE(GPK)                                                                                                          \
+    _Pragma("unroll") for (int k = 0; k < OPT; k++) if (gm[k] > cu[k]) { cu[k] = gm[k]; cgs[k] = (GPK); }
+
     const uint64_t tile_objs = (uint64_t)kAssignThreads * OPT;
     const uint64_t n_tiles = (n_work + tile_objs - 1) / tile_objs;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        uint64_t oi[OPT];
         uint32_t b[OPT], ab[OPT];
         uint64_t best_sc[OPT];
-        uint32_t best_u[OPT], best_gs[OPT], best_cend[OPT];
-        bool valid[OPT];
+        uint32_t best_u[OPT], best_pk[OPT];
 #pragma unroll
         for (int k = 0; k < OPT; k++) {
-            uint64_t t = tile * tile_objs + (uint64_t)k * kAssignThreads + threadIdx.x;
-            valid[k] = t < n_work;
-            oi[k] = valid[k] ? (sel ? (uint64_t)__ldg(sel + t) : t) : 0;
-            uint64_t key = valid[k] ? __ldg(keys + oi[k]) : 0;
-            ObjHash o = obj_hash(key);
+            const uint64_t t = tile * tile_objs + (uint64_t)k * kAssignThreads + threadIdx.x;
+            const bool valid = t < n_work;
+            const uint64_t oi = valid ? (sel ? (uint64_t)__ldg(sel + t) : t) : 0;
+            const uint64_t key = valid ? __ldg(keys + oi) : 0;
+            const ObjHash o = obj_hash(key);
             b[k] = o.b; ab[k] = o.ab;
-            best_sc[k] = ~0ull; best_u[k] = 0; best_gs[k] = 0; best_cend[k] = 0;
+            best_sc[k] = ~0ull; best_u[k] = 0; best_pk[k] = 0;
         }
         uint32_t c = 0, c_start = 0, c_end = 0, c_invw = 0;
         if (n_live) { ClassRec r0 = tab.classes[0], r1 = tab.classes[1]; c_start = r0.start; c_invw = r0.invw; c_end = r1.start; }
@@ -180,61 +202,105 @@ k_assign_hrw_v2(const uint64_t *__restrict__ keys, uint64_t n_work, NodeTabDev t
             uint32_t q = chunk_lo;
             while (q < chunk_hi) {
                 const uint32_t seg_hi = min(c_end, chunk_hi);
+                const uint32_t cend_pk = c_end << 16;
                 if (q == c_start) {
 #pragma unroll
-                    for (int k = 0; k < OPT; k++) { cu[k] = 0; cgs[k] = q; }
+                    for (int k = 0; k < OPT; k++) { cu[k] = 0; cgs[k] = q | cend_pk; }
                 }
-                for (uint32_t g = q; g < seg_hi; g += kGroup) {
-                    const uint32_t ge = min(g + kGroup, seg_hi);
+                uint32_t g = q;
+                for (; g + kGroup <= seg_hi; g += kGroup) {       // full groups
                     uint32_t gm[OPT];
 #pragma unroll
                     for (int k = 0; k < OPT; k++) gm[k] = 0;
-                    uint32_t p = g;
-#pragma unroll 4
-                    for (; p + 1 < ge; p += 2) {
-                        const uint4 r0 = srec[p - chunk_lo], r1 = srec[p + 1 - chunk_lo];
+#pragma unroll 1
+                    for (uint32_t i0 = 0; i0 < kGroup; i0 += BLK) {
+                        const uint4 *s = srec + (g - chunk_lo) + i0;
 #pragma unroll
-                        for (int k = 0; k < OPT; k++)
-                            gm[k] = __vimax3_u32(gm[k], pair_hash(ObjHash{b[k], ab[k]}, r0.x, r0.z, r0.w), pair_hash(ObjHash{b[k], ab[k]}, r1.x, r1.z, r1.w));
+                        for (int i = 0; i < BLK; i += 2) { const uint4 r0 = s[i], r1 = s[i + 1]; RIO_FOLD_PAIR(r0, r1); }
                     }
-                    if (p < ge) {
-                        const uint4 r0 = srec[p - chunk_lo];
+                    RIO_GROUP_DONE(g | cend_pk);
+                }
+                if (g < seg_hi) {                                 // the partial group that ends the segment: 16 + 8 + 4 + 2 + 1
+                    uint32_t gm[OPT];
+#pragma unroll
+                    for (int k = 0; k < OPT; k++) gm[k] = 0;
+                    const uint32_t rem = seg_hi - g;              // 1..31; each power-of-two piece is straight-line
+                    const uint4 *s = srec + (g - chunk_lo);
+#pragma unroll
+                    for (int piece = 16; piece >= 2; piece >>= 1) {
+                        if (rem & piece) {
+#pragma unroll
+                            for (int i = 0; i < piece; i += 2) { const uint4 r0 = s[i], r1 = s[i + 1]; RIO_FOLD_PAIR(r0, r1); }
+                            s += piece;
+                        }
+                    }
+                    if (rem & 1) {
+                        const uint4 r0 = s[0];
 #pragma unroll
                         for (int k = 0; k < OPT; k++) gm[k] = max(gm[k], pair_hash(ObjHash{b[k], ab[k]}, r0.x, r0.z, r0.w));
                     }
-#pragma unroll
-                    for (int k = 0; k < OPT; k++)
-                        if (gm[k] > cu[k]) { cu[k] = gm[k]; cgs[k] = g; }
+                    RIO_GROUP_DONE(g | cend_pk);
                 }
                 q = seg_hi;
                 if (seg_hi == c_end) {
+                    uint64_t sc[OPT];
+#pragma unroll
+                    for (int k = 0; k < OPT; k++) sc[k] = (uint64_t)elog(cu[k]) * c_invw;    // OPT independent chains
 #pragma unroll
                     for (int k = 0; k < OPT; k++) {
-                        const uint64_t sc = (uint64_t)elog(cu[k]) * c_invw;
-                        bool take = sc < best_sc[k] || (sc == best_sc[k] && cu[k] > best_u[k]);
-                        if (sc == best_sc[k] && cu[k] == best_u[k] && best_cend[k] != 0) {
-                            // exact (score, u) tie across two classes: the lower node index wins (spec 3.4); ~2^-32 per class
-                            const ObjHash o{b[k], ab[k]};
-                            take = resolve_in_group(o, tab, cgs[k], c_end, cu[k]) < resolve_in_group(o, tab, best_gs[k], best_cend[k], best_u[k]);
-                        }
-                        if (take) { best_sc[k] = sc; best_u[k] = cu[k]; best_gs[k] = cgs[k]; best_cend[k] = c_end; }
+                        bool take = sc[k] < best_sc[k];
+                        if (sc[k] == best_sc[k]) take = equal_score_takes(b[k], ab[k], grec, cgs[k], best_pk[k], cu[k], best_u[k]);
+                        if (take) { best_sc[k] = sc[k]; best_u[k] = cu[k]; best_pk[k] = cgs[k]; }
                     }
                     c++;
                     if (c < tab.n_classes) { ClassRec r0 = tab.classes[c], r1 = tab.classes[c + 1]; c_start = r0.start; c_invw = r0.invw; c_end = r1.start; }
                 }
             }
         }
+        // recover the node index: re-hash the winning group, last position first so the lowest one wins; no early
+        // exit and positions past the class end predicated off, so the OPT scans of a thread interleave
+        uint32_t nid[OPT];
+#pragma unroll
+        for (int k = 0; k < OPT; k++) nid[k] = kNone;       // stays kNone only without live nodes (best_pk == 0)
+        if (single_chunk) {
+            // Lane L starts at offset L of its group: 32 lanes whose groups are aligned alike (one big class: every
+            // group start is a multiple of 32 records = 512 B) would otherwise hit the same 4 banks 32 ways.  The
+            // scan order then differs per lane, so the LOWEST matching position is kept with a min, not by order.
+            // Positions past the class end may read the kV2Slack records behind the table: never a hit (pos < end).
+            const uint32_t lane = threadIdx.x & 31u;
+            uint32_t fpos[OPT];
+#pragma unroll
+            for (int k = 0; k < OPT; k++) fpos[k] = kNone;
+#pragma unroll 8
+            for (int i = 0; i < (int)kGroup; i++) {
+                const uint32_t off = (lane + (uint32_t)i) & (kGroup - 1);
+#pragma unroll
+                for (int k = 0; k < OPT; k++) {
+                    const uint32_t pos = (best_pk[k] & 0xFFFFu) + off;
+                    const uint4 r = srec[pos];
+                    const bool hit = pair_hash(ObjHash{b[k], ab[k]}, r.x, r.z, r.w) == best_u[k] && pos < (best_pk[k] >> 16);
+                    fpos[k] = min(fpos[k], hit ? pos : kNone);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < OPT; k++) nid[k] = fpos[k] != kNone ? srec[fpos[k]].y : kNone;
+        } else {
+#pragma unroll
+            for (int k = 0; k < OPT; k++) nid[k] = resolve_in_group_global(b[k], ab[k], grec, best_pk[k], best_u[k]);
+        }
 #pragma unroll
         for (int k = 0; k < OPT; k++) {
-            if (!valid[k]) continue;
-            const uint32_t nid = best_cend[k] ? resolve_in_group(ObjHash{b[k], ab[k]}, tab, best_gs[k], best_cend[k], best_u[k]) : kNone;
-            out_idx[oi[k]] = nid;
-            if (nid != kNone) {
-                if (hist_bins) atomicAdd(&shist[nid], 1u);
-                else if (counters) atomicAdd(&counters[nid], 1u);
+            const uint64_t t = tile * tile_objs + (uint64_t)k * kAssignThreads + threadIdx.x;
+            if (t >= n_work) continue;
+            out_idx[sel ? (uint64_t)__ldg(sel + t) : t] = nid[k];
+            if (nid[k] != kNone) {
+                if (hist_bins) atomicAdd(&shist[nid[k]], 1u);
+                else if (counters) atomicAdd(&counters[nid[k]], 1u);
             }
         }
     }
+#undef RIO_FOLD_PAIR
+#undef RIO_GROUP_DONE
     if (hist_bins) {
         __syncthreads();
         if (counters)
@@ -343,7 +409,7 @@ k_assign_affinity_generic(const float *__restrict__ fobj, uint64_t n, const floa
 }
 
 
-// Register-only replay of the assign inner loop (same IMAD / SHF / LOP3 / IMAD / VIMNMX3 mix, no shared or global
+// Register-only replay of the assign inner loop (same IMAD / IMAD / VIMNMX3 mix, no shared or global
 // memory in the loop): its pair rate is the integer-ALU roofline the assign kernel is reported against.
 __global__ void __launch_bounds__(kAssignThreads, 2)
 k_mix_rate(uint32_t iters, uint32_t *sink) {
@@ -354,7 +420,7 @@ k_mix_rate(uint32_t iters, uint32_t *sink) {
     }
     // per-thread (not warp-uniform) node constants, so that the xor stays ONE 3-input LOP3 like in the real loop
     uint32_t s0a = sink[8 + ((threadIdx.x + 64) & 255)] + blockIdx.x, s0b = s0a ^ 0x7F4A7C15u;
-    const uint32_t s1a = sink[8 + ((threadIdx.x + 1) & 255)], s1b = sink[8 + ((threadIdx.x + 2) & 255)];   // opaque, per thread
+    const uint32_t s1a = sink[8 + ((threadIdx.x + 1) & 255)] | 1u, s1b = sink[8 + ((threadIdx.x + 2) & 255)] | 1u;   // opaque, per thread
     const uint32_t s2a = sink[8 + ((threadIdx.x + 3) & 255)], s2b = sink[8 + ((threadIdx.x + 4) & 255)];
     for (uint32_t it = 0; it < iters; it++) {
 #pragma unroll
@@ -450,6 +516,7 @@ static int assign_variant() {
 
 // Objects one full wave of the default rendezvous launch covers (persistent CTAs x objects per tile): host code that
 // pipelines chunks sizes them in whole waves so that no chunk ends on a partially filled wave.
+constexpr int kV2DefaultTune = 432;
 uint64_t assign_wave_objects(int sm_count) { return (uint64_t)sm_count * 3 * kAssignThreads * 4; }
 
 void launch_assign_hrw(const Launch &L, const uint64_t *d_keys, uint64_t n, const NodeTabDev &tab, uint32_t *d_out_idx,
@@ -460,34 +527,38 @@ void launch_assign_hrw(const Launch &L, const uint64_t *d_keys, uint64_t n, cons
     const uint32_t chunk_cap = tab.n_live < 1 ? 1 : (tab.n_live < 8192 ? tab.n_live : 8192);
     const uint32_t hist_bins = (d_counters && tab.n_total <= 8192) ? tab.n_total : 0;
     const size_t smem = (size_t)chunk_cap * sizeof(uint4) + (size_t)hist_bins * 4;
-    if (assign_variant() == 1) {
+    if (assign_variant() == 1 || tab.n_live > kV2MaxLive) {
         cudaFuncSetAttribute(k_assign_hrw<kOPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16 + 8192 * 4);
         const uint64_t tiles = (n_work + (uint64_t)kAssignThreads * kOPT - 1) / ((uint64_t)kAssignThreads * kOPT);
         const int bps = smem > 100 * 1024 ? 1 : 2;
         const uint64_t cap = (uint64_t)L.sm_count * bps;
         k_assign_hrw<kOPT><<<(int)(tiles < cap ? tiles : cap), kAssignThreads, smem, L.stream>>>(d_keys, n_work, tab, d_out_idx, d_counters, d_sel, chunk_cap, hist_bins);
     } else {
-        // RIO_ASSIGN_TUNE="<objects per thread><min CTAs per SM>" selects a compiled tuning point (A/B runs); default 43 (profiles/r01_tune_assign.txt)
+        // RIO_ASSIGN_TUNE="<objects per thread><min CTAs per SM><a|b|c = 8|16|32 straight-line nodes per trip>" selects a
+        // compiled tuning point (A/B runs, tools/tune_assign.py); the default is the fastest of profiles/r01_tune_assign.txt
         const char *t = getenv("RIO_ASSIGN_TUNE");
-        const int tune = (t && t[0] && t[1]) ? (t[0] - '0') * 10 + (t[1] - '0') : 43;
-#define RIO_LAUNCH_V2(OPT_, MINB_)                                                                                                    \
+        const int tune = (t && t[0] && t[1] && t[2]) ? (t[0] - '0') * 100 + (t[1] - '0') * 10 + (t[2] - 'a') : kV2DefaultTune;
+#define RIO_LAUNCH_V2(OPT_, MINB_, BLK_)                                                                                              \
         do {                                                                                                                          \
-            cudaFuncSetAttribute(k_assign_hrw_v2<OPT_, MINB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16 + 8192 * 4);     \
+            cudaFuncSetAttribute(k_assign_hrw_v2<OPT_, MINB_, BLK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (8192 + kV2Slack) * 16 + 8192 * 4); \
             const uint64_t tiles = (n_work + (uint64_t)kAssignThreads * OPT_ - 1) / ((uint64_t)kAssignThreads * OPT_);                \
             int bps = MINB_;                                                                                                          \
-            while (bps > 1 && (size_t)bps * (smem + 1024) > 227u * 1024u) bps--;                                                      \
+            const size_t smem2 = smem + kV2Slack * sizeof(uint4);                                                                     \
+            while (bps > 1 && (size_t)bps * (smem2 + 1024) > 227u * 1024u) bps--;                                                     \
             const uint64_t cap = (uint64_t)L.sm_count * bps;                                                                          \
-            k_assign_hrw_v2<OPT_, MINB_><<<(int)(tiles < cap ? tiles : cap), kAssignThreads, smem, L.stream>>>(d_keys, n_work, tab, d_out_idx, d_counters, \
-                                                                                                            d_sel, chunk_cap, hist_bins); \
+            k_assign_hrw_v2<OPT_, MINB_, BLK_><<<(int)(tiles < cap ? tiles : cap), kAssignThreads, smem2, L.stream>>>(d_keys, n_work, tab, d_out_idx, \
+                                                                                                                  d_counters, d_sel, chunk_cap, hist_bins); \
         } while (0)
         switch (tune) {
-            case 22: RIO_LAUNCH_V2(2, 2); break;
-            case 23: RIO_LAUNCH_V2(2, 3); break;
-            case 24: RIO_LAUNCH_V2(2, 4); break;
-            case 42: RIO_LAUNCH_V2(4, 2); break;
-            case 81: RIO_LAUNCH_V2(8, 1); break;
-            case 82: RIO_LAUNCH_V2(8, 2); break;
-            default: RIO_LAUNCH_V2(4, 3); break;
+            case 430: RIO_LAUNCH_V2(4, 3, 8); break;
+            case 431: RIO_LAUNCH_V2(4, 3, 16); break;
+            case 432: RIO_LAUNCH_V2(4, 3, 32); break;
+            case 420: RIO_LAUNCH_V2(4, 2, 8); break;
+            case 422: RIO_LAUNCH_V2(4, 2, 32); break;
+            case 820: RIO_LAUNCH_V2(8, 2, 8); break;
+            case 822: RIO_LAUNCH_V2(8, 2, 32); break;
+            case 240: RIO_LAUNCH_V2(2, 4, 8); break;
+            default: RIO_LAUNCH_V2(4, 3, 32); break;
         }
 #undef RIO_LAUNCH_V2
     }

@@ -11,7 +11,7 @@ namespace rio {
 struct __align__(16) NodeRec {
     uint32_t s0;    // lo32(seed)
     uint32_t nidx;  // interned node index (what the directory stores)
-    uint32_t s1;    // hi32(seed)
+    uint32_t s1;    // hi32(seed) | 1: the per-node odd multiplier of the second multiply-add
     uint32_t s2;    // lo32(mix64(seed ^ kSaltNode2))
 };
 struct ClassRec {
@@ -25,7 +25,7 @@ struct NodeTabDev {
     uint32_t n_classes;
     uint32_t n_total;          // interned nodes (size of counter / by-index arrays)
     // by-interned-index arrays (n_total entries) for the kernels that gather by node index
-    const uint4 *by_idx;       // {s0, invw (0 = not live), s1, s2}
+    const uint4 *by_idx;       // {s0, invw (0 = not live), hi32(seed)|1, s2}
 };
 
 // ---- directory: open addressing, 16-byte AoS slots ------------------------------------------------------

@@ -72,12 +72,11 @@ RIO_HD ObjHash obj_hash(uint64_t key) {
     return o;
 }
 
-// u(key, node): (s0, s1) = (lo32, hi32) of the node seed, s2 = lo32(mix64(seed ^ kSaltNode2)).
-// SASS per pair: IMAD, SHF, LOP3 (3-input xor), IMAD.
-RIO_HD uint32_t pair_hash(ObjHash o, uint32_t s0, uint32_t s1, uint32_t s2) {
+// u(key, node), spec v3: s0 = lo32(seed), m = hi32(seed) | 1 (stored pre-or'ed in the node records),
+// s2 = lo32(mix64(seed ^ kSaltNode2)).  SASS per pair: IMAD, IMAD.
+RIO_HD uint32_t pair_hash(ObjHash o, uint32_t s0, uint32_t m, uint32_t s2) {
     const uint32_t p = s0 * o.b + o.ab;
-    const uint32_t q = p ^ (p >> 15) ^ s1;
-    return q * kPairC1 + s2;
+    return p * m + s2;
 }
 
 RIO_HD uint32_t inv_weight(uint32_t w) { return w ? 0xFFFFFFFFu / w : 0u; }

@@ -57,8 +57,7 @@ def pair_hash(key, seed):
     s0, s1 = seed & M32, seed >> 32
     s2 = mix64(seed ^ 0xA0761D6478BD642F) & M32
     p = (s0 * b + ab) & M32
-    q = p ^ (p >> 15) ^ s1
-    return (q * 0x9E3779B1 + s2) & M32
+    return (p * (s1 | 1) + s2) & M32
 
 
 def inv_weight(w):

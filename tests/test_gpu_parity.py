@@ -195,6 +195,22 @@ def test_ragged_node_counts(gp, oracle, M, uniform, variant):
     assert (got == oracle.assign_hrw(keys, seeds, w, threads=8)).all()
 
 
+@pytest.mark.parametrize("variant", ["2", "1"])
+@pytest.mark.parametrize("M,n", [(9000, 6001), (70000, 1501)])
+def test_node_tables_larger_than_one_shared_memory_chunk(gp, oracle, M, n, variant):
+    """M = 9000: the table is streamed through shared memory in two chunks and the winner is re-hashed from global
+    memory; M = 70000 exceeds the 16-bit positions of k_assign_hrw_v2, so the launcher must route to k_assign_hrw."""
+    os.environ["RIO_ASSIGN_VARIANT"] = variant
+    try:
+        p = provider(gp)
+        _, seeds, w = _nodes(p, oracle, M)
+        keys = oracle.synth_keys(n, 5)
+        got = p.assign_batch(keys)
+    finally:
+        os.environ.pop("RIO_ASSIGN_VARIANT", None)
+    assert (got == oracle.assign_hrw(keys, seeds, w, threads=8)).all()
+
+
 def test_many_weight_classes_and_big_weights(gp, oracle):
     p = provider(gp)
     addrs, seeds, _ = oracle.synth_nodes(300)
