@@ -131,7 +131,7 @@ struct rio_placement {
     uint32_t K = 0;
     bool tab_dirty = true;
     TabBufs tabs, tabs_masked;
-    DevBuf d_node_state, d_live, d_fnode, d_fnode_c, d_nidx_map;
+    DevBuf d_node_state, d_live, d_fnode, d_fnode_c, d_fnode_g, d_nidx_map;
     uint32_t aff_live = 0, aff_pad = 0;   // compacted live-node operands of the tcgen05 affinity kernel
 
     DirDev dir{};
@@ -281,7 +281,15 @@ void ensure_tab(rio_placement *h) {
         std::vector<float> fc((size_t)pad * 16, 0.f);
         for (uint32_t q = 0; q < nl; q++) if (h->nodes[map[q]].feat.size() == 16) std::copy(h->nodes[map[q]].feat.begin(), h->nodes[map[q]].feat.end(), fc.begin() + (size_t)q * 16);
         map.resize(pad, kNone);
+        // the same rows regrouped as [group of 8 nodes][16-byte piece][node in group] for k_affinity_resolve
+        std::vector<float> fg(fc.size());
+        for (uint32_t g8 = 0; g8 < pad / 8; g8++)
+            for (uint32_t k4 = 0; k4 < 4; k4++)
+                for (uint32_t r8 = 0; r8 < 8; r8++)
+                    std::copy_n(fc.begin() + ((size_t)g8 * 8 + r8) * 16 + k4 * 4, 4, fg.begin() + (((size_t)g8 * 4 + k4) * 8 + r8) * 4);
         h->d_fnode_c.ensure(fc.size() * 4, st);
+        h->d_fnode_g.ensure(fg.size() * 4, st);
+        CUDA_TRY(cudaMemcpyAsync(h->d_fnode_g.p, fg.data(), fg.size() * 4, cudaMemcpyHostToDevice, st));
         h->d_nidx_map.ensure(map.size() * 4, st);
         CUDA_TRY(cudaMemcpyAsync(h->d_fnode_c.p, fc.data(), fc.size() * 4, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(h->d_nidx_map.p, map.data(), map.size() * 4, cudaMemcpyHostToDevice, st));
@@ -362,7 +370,7 @@ void run_affinity(rio_placement *h, const float *d_fobj, uint64_t n, uint32_t *d
     const bool want_umma = !(v && v[0] == 'f');
     if (!h->aff_live && h->K == 16 && h->tabs.tab.n_live == 0) { launch_fill_u32(h->L(), d_out_idx, n, kNone); return; }
     if (want_umma && h->K == 16 && h->aff_live && h->aff_pad <= affinity_umma_max_nodes()) {
-        if (launch_assign_affinity_umma(h->L(), d_fobj, n, h->d_fnode_c.as<float>(), h->d_nidx_map.as<uint32_t>(), h->aff_live, h->aff_pad, h->tabs.tab.n_total, d_out_idx, d_out_cost,
+        if (launch_assign_affinity_umma(h->L(), d_fobj, n, h->d_fnode_c.as<float>(), h->d_fnode_g.as<float>(), h->d_nidx_map.as<uint32_t>(), h->aff_live, h->aff_pad, h->tabs.tab.n_total, d_out_idx, d_out_cost,
                                         d_counters))
             return;
     }
@@ -519,7 +527,7 @@ void rio_cuda_destroy(rio_placement *h) {
         cudaFree(h->xchg_mine);
     }
     DevBuf *bufs[] = {&h->tabs.recs, &h->tabs.classes, &h->tabs.by_idx, &h->tabs_masked.recs, &h->tabs_masked.classes, &h->tabs_masked.by_idx,
-                      &h->d_node_state, &h->d_live, &h->d_fnode, &h->d_fnode_c, &h->d_nidx_map, &h->s_keys, &h->s_idx, &h->s_idx2, &h->s_sel, &h->s_slots, &h->s_keys2, &h->s_feats,
+                      &h->d_node_state, &h->d_live, &h->d_fnode, &h->d_fnode_c, &h->d_fnode_g, &h->d_nidx_map, &h->s_keys, &h->s_idx, &h->s_idx2, &h->s_sel, &h->s_slots, &h->s_keys2, &h->s_feats,
                       &h->s_packed, &h->s_offsets, &h->s_cost, &h->s_misc, &h->s_flush, &h->s_gather};
     for (DevBuf *b : bufs) b->release(h->stream);
     if (h->dir.slots) cudaFreeAsync(h->dir.slots, h->stream);

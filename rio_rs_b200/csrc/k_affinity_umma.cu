@@ -320,64 +320,81 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_affinity_umma(UmmaParams P)
     }
 }
 
-// Second pass: the 8 candidates of each object's winning group, re-evaluated in fp32.  One warp per object: the 8 candidate
-// node rows are 512 contiguous bytes, so lane l = 4*r + c loads the 16-byte piece c of candidate row r (ONE coalesced
-// 128-bit load per lane, four 128-byte lines per object -- the per-thread version of this loop touched 32 scattered sectors
-// per load and was L1-wavefront bound at 1.17 ms, profiles/r01_launches_final.csv), multiplies it with piece c of the
-// object's own row, and two xor-shuffles finish the 16-term dot product; three more pick the smallest (cost, position).
+// Second pass: the 8 candidates of each object's winning group, re-evaluated in fp32 with the summation order of
+// k_assign_affinity (fmaf over k = 0..15).  EIGHT lanes per object, four objects per warp trip: lane 8q + r scores
+// candidate r of object q.  `fnode_g` is the node features regrouped on the host as [group][16-byte piece k][candidate r],
+// so the k-th load of the eight lanes of an object is one 128-byte line (4 lines per object, like the contiguous rows),
+// and the object's own row is a broadcast inside the 8 lanes.  Three xor-shuffle steps pick the smallest
+// (cost, position).  The earlier one-warp-per-object version issued 50 warp instructions per object and was
+// issue-bound at 0.79 ms for 10 M objects (profiles/r01_launches_final.csv); this one issues ~16.
 // in/out: idx[row] holds the group on entry, the interned node index on exit.
 __global__ void __launch_bounds__(256)
-k_affinity_resolve(const float *__restrict__ fobj, uint64_t n, const float *__restrict__ fnode_c, const uint32_t *__restrict__ nidx_map, uint32_t n_live,
+k_affinity_resolve(const float *__restrict__ fobj, uint64_t n, const float *__restrict__ fnode_g, const uint32_t *__restrict__ nidx_map, uint32_t n_live,
                    uint32_t *__restrict__ idx, float *__restrict__ out_cost, uint32_t *__restrict__ counters, uint32_t hist_bins) {
     extern __shared__ uint32_t shist[];
     for (uint32_t j = threadIdx.x; j < hist_bins; j += blockDim.x) shist[j] = 0;
     __syncthreads();
-    const uint32_t lane = threadIdx.x & 31, r = lane >> 2, c = lane & 3;
+    const uint32_t lane = threadIdx.x & 31, q = lane >> 3, r = lane & 7;
     const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    const float4 *fobj4 = reinterpret_cast<const float4 *>(fobj) + c;        // piece c of an object row: + 4*row
-    const float4 *fnode4 = reinterpret_cast<const float4 *>(fnode_c) + lane;  // piece c of candidate r of group g: + 32*g
-    constexpr int U = 4;   // objects in flight per warp
-    for (uint64_t base = warp0 * U; base < n; base += nwarps * U) {
-        float acc[U];
-        uint32_t grp[U];
+    const float4 *fobj4 = reinterpret_cast<const float4 *>(fobj);
+    const float4 *fnode4 = reinterpret_cast<const float4 *>(fnode_g) + r;     // piece k of candidate r of group g: + (4*g + k) * 8
+    // Software pipeline, one trip ahead: the group index and the object's row of the NEXT trip are in flight (HBM latency)
+    // while the current trip reads its candidates (L1/L2 hits) and reduces; without it a warp has one dependent chain
+    // idx -> node rows -> dot product in flight and the kernel is latency bound (profiles/r01_ncu_affinity_resolve_v2.json).
+    uint64_t base = warp0 * 4;
+    bool mine = base + q < n;
+    uint64_t row = mine ? base + q : n - 1;                                     // clamp: the tail recomputes the last object
+    uint32_t g = 0;
+    float4 o[4] = {};
+    if (base < n) {
+        g = __ldg(idx + row);
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const uint64_t row = base + u < n ? base + u : n - 1;               // clamp: the tail recomputes the last object
-            grp[u] = __ldg(idx + row);                                          // one address for the whole warp
-            const float4 fo = __ldg(fobj4 + row * 4);
-            const float4 x = __ldg(fnode4 + (size_t)grp[u] * 32);              // rows beyond n_live are zero padding
-            float a = fo.x * x.x;
-            a = fmaf(fo.y, x.y, a); a = fmaf(fo.z, x.z, a); a = fmaf(fo.w, x.w, a);
-            acc[u] = a;
-        }
-        uint32_t my_p = kNone;      // lane u (< U) ends up owning object base+u: its winning position and cost
-        float my_c = 0.f;
+        for (int k = 0; k < 4; k++) o[k] = __ldg(fobj4 + row * 4 + k);
+    }
+    for (; base < n; base += nwarps * 4) {
+        const uint64_t nbase = base + nwarps * 4;
+        const bool nmine = nbase + q < n;
+        const uint64_t nrow = nmine ? nbase + q : n - 1;
+        uint32_t ng = 0;
+        float4 no[4] = {};
+        if (nbase < n) {                                                        // warp-uniform
+            ng = __ldg(idx + nrow);     // safe to read ahead: idx[nrow] is rewritten only by the trip that owns nrow (this warp, later)
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            float a = acc[u];
-            a += __shfl_xor_sync(0xFFFFFFFFu, a, 1);
-            a += __shfl_xor_sync(0xFFFFFFFFu, a, 2);                            // every lane of a candidate row holds its dot product
-            const uint32_t p = grp[u] * 8 + r;
-            // order-preserving integer image of cost = -dot (+inf for padding), minimum by one warp reduction;
-            // the lowest lane holding the minimum is the lowest candidate position (ties -> lowest node)
-            const uint32_t bits = p < n_live ? __float_as_uint(-a) : 0x7F800000u;
-            const int key = (int)(bits ^ ((uint32_t)((int)bits >> 31) & 0x7FFFFFFFu));
-            const int kmin = __reduce_min_sync(0xFFFFFFFFu, key);
-            const uint32_t first = __ffs(__ballot_sync(0xFFFFFFFFu, key == kmin)) - 1;
-            const uint32_t bp = __shfl_sync(0xFFFFFFFFu, p < n_live ? p : kNone, first);
-            const float bc = __shfl_sync(0xFFFFFFFFu, -a, first);
-            if (lane == (uint32_t)u) { my_p = bp; my_c = bc; }
+            for (int k = 0; k < 4; k++) no[k] = __ldg(fobj4 + nrow * 4 + k);
         }
-        // lanes 0..U-1 finish one object each: four independent map lookups, one 16-byte store
-        if (lane < U && base + lane < n) {
-            const uint32_t nid = my_p == kNone ? kNone : __ldg(nidx_map + my_p);
-            idx[base + lane] = nid;
-            if (out_cost) out_cost[base + lane] = my_p == kNone ? 0.f : my_c;
+        const float4 *fn = fnode4 + (size_t)g * 32;
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float4 x = __ldg(fn + k * 8);                                 // rows beyond n_live are zero padding
+            a = fmaf(o[k].x, x.x, a); a = fmaf(o[k].y, x.y, a); a = fmaf(o[k].z, x.z, a); a = fmaf(o[k].w, x.w, a);
+        }
+        // order-preserving integer image of cost = -dot (+inf for padding); minimum of (key, position) over the 8 lanes
+        uint32_t p = g * 8 + r;
+        const uint32_t bits = p < n_live ? __float_as_uint(-a) : 0x7F800000u;
+        int key = (int)(bits ^ ((uint32_t)((int)bits >> 31) & 0x7FFFFFFFu));
+        if (p >= n_live) p = kNone;
+#pragma unroll
+        for (int d = 4; d >= 1; d >>= 1) {
+            const int ok = __shfl_xor_sync(0xFFFFFFFFu, key, d);
+            const uint32_t op = __shfl_xor_sync(0xFFFFFFFFu, p, d);
+            if (ok < key || (ok == key && op < p)) { key = ok; p = op; }
+        }
+        if (r == 0 && mine) {
+            const uint32_t nid = p == kNone ? kNone : __ldg(nidx_map + p);
+            idx[row] = nid;
+            if (out_cost) {
+                const uint32_t kb = (uint32_t)key;
+                out_cost[row] = p == kNone ? 0.f : __uint_as_float(kb ^ ((uint32_t)((int)kb >> 31) & 0x7FFFFFFFu));   // the image is an involution
+            }
             if (nid != kNone) {
                 if (hist_bins) atomicAdd(&shist[nid], 1u);
                 else if (counters) atomicAdd(&counters[nid], 1u);
             }
         }
+        mine = nmine; row = nrow; g = ng;
+#pragma unroll
+        for (int k = 0; k < 4; k++) o[k] = no[k];
     }
     if (hist_bins) {
         __syncthreads();
@@ -397,7 +414,7 @@ void affinity_umma_set_timing_buffer(unsigned long long *d) { g_umma_timing = d;
 // Largest padded live-node count whose operands fit in shared memory beside the A stages.
 uint32_t affinity_umma_max_nodes() { return ((227u * 1024u - kBarBytes - kStages * kAStageBytes) / 96u) / 256u * 256u; }
 
-bool launch_assign_affinity_umma(const Launch &L, const float *d_fobj, uint64_t n, const float *d_fnode_c, const uint32_t *d_nidx_map, uint32_t n_live,
+bool launch_assign_affinity_umma(const Launch &L, const float *d_fobj, uint64_t n, const float *d_fnode_c, const float *d_fnode_g, const uint32_t *d_nidx_map, uint32_t n_live,
                                  uint32_t m_pad, uint32_t n_total, uint32_t *d_out_idx, float *d_out_cost, uint32_t *d_counters) {
     if (!n || !n_live) return false;
     const bool small = m_pad <= 64;
@@ -426,8 +443,8 @@ bool launch_assign_affinity_umma(const Launch &L, const float *d_fobj, uint64_t 
     RIO_COUNT_LAUNCH(L);
     {
         const uint32_t bins = (d_counters && n_total <= 8192) ? n_total : 0;
-        const uint64_t blocks = (n + 31) / 32, cap = (uint64_t)L.sm_count * 8;   // one warp per 4 objects, 8 warps per CTA
-        k_affinity_resolve<<<(int)(blocks < cap ? blocks : cap), 256, (size_t)bins * 4, L.stream>>>(d_fobj, n, d_fnode_c, d_nidx_map, n_live, d_out_idx, d_out_cost, d_counters,
+        const uint64_t blocks = (n + 31) / 32, cap = (uint64_t)L.sm_count * 8;   // 4 objects per warp trip, 8 warps per CTA
+        k_affinity_resolve<<<(int)(blocks < cap ? blocks : cap), 256, (size_t)bins * 4, L.stream>>>(d_fobj, n, d_fnode_g, d_nidx_map, n_live, d_out_idx, d_out_cost, d_counters,
                                                                                           bins);
         RIO_COUNT_LAUNCH(L);
     }

@@ -516,8 +516,8 @@ static int assign_variant() {
 
 // Objects one full wave of the default rendezvous launch covers (persistent CTAs x objects per tile): host code that
 // pipelines chunks sizes them in whole waves so that no chunk ends on a partially filled wave.
-constexpr int kV2DefaultTune = 432;
-uint64_t assign_wave_objects(int sm_count) { return (uint64_t)sm_count * 3 * kAssignThreads * 4; }
+constexpr int kV2DefaultTune = 532;   // 5 objects per thread, 3 CTAs per SM, 32-node straight-line groups (profiles/r01_tune_assign.txt)
+uint64_t assign_wave_objects(int sm_count) { return (uint64_t)sm_count * 3 * kAssignThreads * 5; }
 
 void launch_assign_hrw(const Launch &L, const uint64_t *d_keys, uint64_t n, const NodeTabDev &tab, uint32_t *d_out_idx,
                        uint32_t *d_counters, const uint32_t *d_sel, uint64_t n_sel) {
@@ -558,7 +558,11 @@ void launch_assign_hrw(const Launch &L, const uint64_t *d_keys, uint64_t n, cons
             case 820: RIO_LAUNCH_V2(8, 2, 8); break;
             case 822: RIO_LAUNCH_V2(8, 2, 32); break;
             case 240: RIO_LAUNCH_V2(2, 4, 8); break;
-            default: RIO_LAUNCH_V2(4, 3, 32); break;
+            case 342: RIO_LAUNCH_V2(3, 4, 32); break;
+            case 332: RIO_LAUNCH_V2(3, 3, 32); break;
+            case 622: RIO_LAUNCH_V2(6, 2, 32); break;
+            case 522: RIO_LAUNCH_V2(5, 2, 32); break;
+            case 532: default: RIO_LAUNCH_V2(5, 3, 32); break;
         }
 #undef RIO_LAUNCH_V2
     }

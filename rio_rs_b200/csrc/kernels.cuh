@@ -54,7 +54,7 @@ void launch_assign_affinity(const Launch &L, const float *d_fobj, uint64_t n, co
 // tcgen05/TMEM path for K == 16 (k_affinity_umma.cu); returns false when the shape is not supported (caller falls back to FFMA kernel)
 uint32_t affinity_umma_max_nodes();
 void affinity_umma_set_timing_buffer(unsigned long long *d);
-bool launch_assign_affinity_umma(const Launch &L, const float *d_fobj, uint64_t n, const float *d_fnode_c, const uint32_t *d_nidx_map, uint32_t n_live,
+bool launch_assign_affinity_umma(const Launch &L, const float *d_fobj, uint64_t n, const float *d_fnode_c, const float *d_fnode_g, const uint32_t *d_nidx_map, uint32_t n_live,
                                  uint32_t m_pad, uint32_t n_total, uint32_t *d_out_idx, float *d_out_cost, uint32_t *d_counters);
 uint64_t launch_mix_rate(const Launch &L, uint32_t iters, uint32_t *d_sink);
 void launch_synth_keys(const Launch &L, uint64_t *d_keys, uint64_t first, uint64_t n, uint64_t seed);

@@ -19,7 +19,7 @@ for uniform in (False, True):
         s.synth_keys(0, n, 1 + k)
         sets.append(s)
     want = O.assign_hrw(O.synth_keys(20000, 1), seeds, w, threads=8)
-    for variant, tune in [("1", "43c"), ("2", "43a"), ("2", "43b"), ("2", "43c"), ("2", "42a"), ("2", "42c"), ("2", "82a"), ("2", "82c"), ("2", "24a")]:
+    for variant, tune in [("1", "43c"), ("2", "43a"), ("2", "43b"), ("2", "43c"), ("2", "42a"), ("2", "42c"), ("2", "82a"), ("2", "34c"), ("2", "33c"), ("2", "62c"), ("2", "52c"), ("2", "53c")]:
         os.environ["RIO_ASSIGN_VARIANT"] = variant
         os.environ["RIO_ASSIGN_TUNE"] = tune
         for i in range(3):
