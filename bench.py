@@ -45,7 +45,7 @@ HBM_FALLBACK_GBS = 6650.0
 
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the assign kernel from the committed ncu capture."""
-    p = os.path.join(ROOT, "profiles", "r01_ncu_assign_v2.json")
+    p = os.path.join(ROOT, "profiles", "r01_ncu_assign_v3.json")
     try:
         return float(json.load(open(p))["dram_bytes_per_launch"]), os.path.relpath(p, ROOT)
     except Exception:
@@ -257,6 +257,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        # stdout carries ONE JSON line: when the box sets NCCL_DEBUG (even just VERSION) NCCL's banner would land there
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
