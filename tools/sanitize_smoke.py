@@ -19,6 +19,12 @@ assert (p.assign_batch(keys) == want).all()                         # k_assign_h
 os.environ["RIO_ASSIGN_VARIANT"] = "1"
 assert (p.assign_batch(keys) == want).all()                         # k_assign_hrw
 os.environ.pop("RIO_ASSIGN_VARIANT")
+big = R.GpuObjectPlacement(device=0)                                # full 32-node groups + 16/8/4/2/1 tails + rotated index scan
+for M, uniform in ((203, True), (333, False)):
+    a3, s3, w3 = O.synth_nodes(M, uniform=uniform)
+    big.set_nodes(a3, w3)
+    assert (big.assign_batch(keys[:3000]) == O.assign_hrw(keys[:3000], s3, w3)).all()
+del big
 assert (p.place_batch(keys, "hrw") == want).all()                   # lookup, classify, assign(sel), gather, upsert (with growth + rehash)
 assert (p.lookup_many(keys) == want).all()
 ids = [("Obj", str(i)) for i in range(3000)]
