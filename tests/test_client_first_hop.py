@@ -1,0 +1,100 @@
+"""Client-side deterministic first hop (include/rio_client.h): bit-exact against the oracle's
+weighted rendezvous hash, the reference client's behaviour around it (client/mod.rs:235-267), and the redirect rate
+the reference's random pick would have had.  CPU only."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from rio_rs_b200 import client as CL
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_exported_and_bound():
+    hdr = open(os.path.join(ROOT, "include", "rio_client.h")).read()
+    declared = set(re.findall(r"\b(rio_client_[a-z_]+)\s*\(", hdr))
+    assert declared == set(CL.SIGNATURES), declared ^ set(CL.SIGNATURES)
+    L = CL.lib()
+    for name in declared:
+        assert hasattr(L, name)
+
+
+@pytest.mark.parametrize("M,uniform", [(1, True), (4, True), (64, False), (300, False), (1024, False), (1024, True)])
+def test_first_hop_equals_oracle_rendezvous(M, uniform):
+    addrs, seeds, w = O.synth_nodes(M, uniform=uniform)
+    fh = CL.FirstHop(addrs, w)
+    keys = O.synth_keys(20000 if M <= 300 else 6000, 3)
+    assert (fh.first_hop_batch(keys) == O.assign_hrw(keys, seeds, w, threads=4)).all()
+
+
+def test_dead_nodes_raw_keys_and_no_servers():
+    addrs, seeds, w = O.synth_nodes(16)
+    w2 = w.copy()
+    w2[::2] = 0                                               # weight 0 == not live
+    fh = CL.FirstHop(addrs, w2)
+    keys = np.concatenate([np.arange(0, 3000, dtype=np.uint64), np.array([2**64 - 1, 2**64 - 2, 0], dtype=np.uint64)])
+    assert (fh.first_hop_batch(keys) == O.assign_hrw(keys, seeds, w2)).all()
+    empty = CL.FirstHop([])
+    assert (empty.first_hop_batch(keys[:10]) == CL.NONE).all()
+    with pytest.raises(CL.NoServersAvailable):                # ClientError::NoServersAvailable (client/mod.rs:260-261)
+        empty.get_service_object_address("Obj", "1")
+
+
+def test_string_level_key_is_the_directory_key():
+    assert CL.object_key("Obj", "7") == O.object_key("Obj", "7")
+    assert CL.object_key("a.b", "c") == CL.object_key("a", "b.c")   # same aliasing as format!("{}.{}") (local.rs:26-29)
+    addrs, seeds, w = O.synth_nodes(64)
+    fh = CL.FirstHop(addrs, w)
+    ids = [("Obj", str(i)) for i in range(500)]
+    keys = np.array([O.object_key(t, i) for t, i in ids], dtype=np.uint64)
+    want = O.assign_hrw(keys, seeds, w)
+    assert [fh.get_service_object_address(t, i) for t, i in ids] == [addrs[j] for j in want]
+
+
+def test_cache_hit_precedes_the_hash_and_is_bounded():
+    addrs, _, w = O.synth_nodes(8)
+    fh = CL.FirstHop(addrs, w, cache_size=3)
+    owner = fh.get_service_object_address("Obj", "1")
+    other = next(a for a in addrs if a != owner)
+    fh.record_redirect("Obj", "1", other)                     # the server corrected us (tower_services.rs:158-168)
+    assert fh.get_service_object_address("Obj", "1") == other
+    for i in range(2, 6):
+        fh.record_redirect("Obj", str(i), other)
+    assert fh.get_service_object_address("Obj", "1") == owner  # evicted (LRU limit) -> back to the hash
+
+
+def test_membership_change_moves_only_the_leavers_objects():
+    addrs, seeds, w = O.synth_nodes(64)
+    fh = CL.FirstHop(addrs, w)
+    keys = O.synth_keys(20000, 9)
+    before = fh.first_hop_batch(keys)
+    w2 = w.copy()
+    w2[17] = 0
+    fh.set_active_servers(addrs, w2)                          # fetch_active_servers replaces the whole view
+    after = fh.first_hop_batch(keys)
+    assert ((before != after) == (before == 17)).all() and (after != 17).all()
+
+
+def test_redirect_rate_against_the_reference_pick():
+    """Objects placed by the servers with policy "hrw" (== the oracle's rendezvous assignment): the reference's uniform
+    random first hop (client/mod.rs:254-263) is wrong (M-1)/M of the time, the rendezvous first hop never."""
+    M = 64
+    addrs, seeds, w = O.synth_nodes(M)
+    keys = O.synth_keys(50000, 4)
+    owner = O.assign_hrw(keys, seeds, w, threads=4)
+    fh = CL.FirstHop(addrs, w)
+    assert int((fh.first_hop_batch(keys) != owner).sum()) == 0
+    rnd = np.random.default_rng(0).integers(0, M, len(keys))
+    rate = float((rnd != owner).mean())
+    assert abs(rate - (M - 1) / M) < 0.01
+
+
+def test_server_product_does_not_use_the_client_library():
+    for f in ("provider.py", "_native.py", "parallel.py", "durable.py", "__init__.py"):
+        src = open(os.path.join(ROOT, "rio_rs_b200", f)).read()
+        assert "librio_client" not in src and "rio_client" not in src and "from .client" not in src and "import client" not in src, f
+    eng = "".join(open(os.path.join(ROOT, "rio_rs_b200", "csrc", f)).read() for f in ("engine.cu", "resolver.cu"))
+    assert "rio_client" not in eng

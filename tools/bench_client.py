@@ -1,0 +1,31 @@
+"""Client-side first hop (include/rio_client.h): cost per resolve on one host core, and the redirect rate it removes.
+CPU only -- run anywhere:  python tools/bench_client.py"""
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import pyoracle as O
+from rio_rs_b200 import client as CL
+
+try:
+    cpu = [l.split(":")[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name")][0]
+except Exception:
+    cpu = "unknown"
+print("host: %s, 1 thread" % cpu)
+for M in (4, 64, 1024):
+    addrs, seeds, w = O.synth_nodes(M)
+    fh = CL.FirstHop(addrs, w)
+    n = 2_000_000 // M + 1000
+    keys = O.synth_keys(n, 1)
+    fh.first_hop_batch(keys[:100])
+    t = time.perf_counter()
+    got = fh.first_hop_batch(keys)
+    dt = time.perf_counter() - t
+    owner = O.assign_hrw(keys, seeds, w, threads=4)
+    wrong = int((got != owner).sum())
+    rnd = np.random.default_rng(0).integers(0, M, n)
+    print("M=%4d: %8.1f ns per first hop (%5.2f ns per node), redirects: rendezvous %d / %d, uniform-random pick (client/mod.rs:254-263) %.1f %%"
+          % (M, 1e9 * dt / n, 1e9 * dt / n / M, wrong, n, 100.0 * float((rnd != owner).mean())))
