@@ -10,7 +10,7 @@
  * (rio-rs/src/service.rs:241-253) behind a CRUD directory (rio-rs/src/object_placement/mod.rs:38-56).
  * No reference file, test or dependency defines a rendezvous hash, weights, affinity costs or
  * bounded-load rounds, so this file is a restatement of the spec written in DESIGN.md section 3
- * ("Solver spec v1"), written independently of the CUDA implementation (no shared headers), and
+ * ("Solver spec"; pair hash at revision v3), written independently of the CUDA implementation (no shared headers), and
  * cross-checked by a third, pure-Python implementation in tests/spec_py.py plus the committed
  * golden vectors under tests/golden/.
  *
@@ -52,7 +52,6 @@ static void par_for(size_t n, int threads, range_fn fn, void *ctx) {
 #define SALT_NODE2 0xA0761D6478BD642Full
 #define SALT_SPILL 0x2545F4914F6CDD1Dull
 #define GOLDEN64   0x9E3779B97F4A7C15ull
-#define PAIR_C1    0x9E3779B1u
 #define LOG_K0 0x71376877u
 #define LOG_K1 0x44D58AB6u
 #define LOG_K2 0x2677DB2Eu

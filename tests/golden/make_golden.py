@@ -1,6 +1,6 @@
 """Generates tests/golden/solver_v1.json from the pure-Python spec (tests/spec_py.py).
 
-The reference has no solver, so these vectors pin *this repo's* spec v1 (parity unpinned vs rio-rs);
+The reference has no solver, so these vectors pin *this repo's* spec (pair hash at revision v3 -- the file name is the golden FORMAT version; parity unpinned vs rio-rs);
 they exist so that neither the C oracle nor the CUDA kernels can drift silently between rounds.
 Run: python tests/golden/make_golden.py
 """
