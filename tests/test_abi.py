@@ -72,3 +72,13 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "pyoracle" not in src and "rio_oracle" not in src and "directory_model" not in src, f
+
+
+def test_rust_ffi_declarations_cover_the_headers():
+    """The Rust crates are source only (no cargo here), so at least keep their extern blocks in step with include/*.h."""
+    import re
+
+    for header, crate, prefix in (("rio_cuda.h", "rio-cuda-sys", "rio_cuda_"), ("rio_client.h", "rio-client-first-hop", "rio_client_")):
+        declared = set(re.findall(r"\b(%s[a-z0-9_]+)\s*\(" % prefix, open(os.path.join(ROOT, "include", header)).read()))
+        rust = set(re.findall(r"fn (%s[a-z0-9_]+)\s*\(" % prefix, open(os.path.join(ROOT, "rust", crate, "src", "lib.rs")).read()))
+        assert declared == rust, (header, declared ^ rust)
