@@ -70,6 +70,32 @@ def test_pair_hash_and_hrw_match_python(oracle):
     assert not (set(idx2.tolist()) & closed) and all(w2[j] for j in idx2)
 
 
+def test_exact_ties_go_to_the_lowest_index(oracle):
+    """Spec 3.4: lexicographic minimum of (E(u)*r, ~u, j).  Hashed seeds never tie at test sizes (2^-32 per pair), so the
+    rule is forced here with DUPLICATED seeds: equal weight => equal (score, u) => the lower index must win; a heavier
+    twin must win on the score; a dead or closed twin must not shadow the live one."""
+    _, seeds, w = oracle.synth_nodes(12, uniform=True)
+    seeds = seeds.copy()
+    seeds[7] = seeds[2]          # twins 2 and 7
+    seeds[11] = seeds[4]         # twins 4 and 11
+    keys = oracle.synth_keys(4000, 8)
+    idx = oracle.assign_hrw(keys, seeds, w)
+    assert idx.tolist() == [sp.hrw(int(k), [int(s) for s in seeds], [int(x) for x in w]) for k in keys]
+    assert not (set(idx.tolist()) & {7, 11}) and {2, 4} <= set(idx.tolist())
+    w2 = w.copy()
+    w2[7] = 3                    # heavier twin: same u, smaller E(u)*r
+    idx2 = oracle.assign_hrw(keys, seeds, w2)
+    assert 2 not in set(idx2.tolist()) and 7 in set(idx2.tolist())
+    w3 = w.copy()
+    w3[2] = 0                    # dead lower twin: 7 inherits exactly its objects
+    idx3 = oracle.assign_hrw(keys, seeds, w3)
+    assert (idx3[idx == 2] == 7).all() and (idx3[idx != 2] == idx[idx != 2]).all()
+    mask = np.zeros(1, dtype=np.uint32)
+    mask[0] = np.uint32(1 << 4)  # closed lower twin (bounded-load rounds)
+    idx4 = oracle.assign_hrw(keys, seeds, w, mask=mask)
+    assert (idx4[idx == 4] == 11).all()
+
+
 def test_no_live_node_gives_none(oracle):
     _, seeds, w = oracle.synth_nodes(4)
     idx = oracle.assign_hrw(oracle.synth_keys(5, 2), seeds, np.zeros(4, dtype=np.uint32))
