@@ -225,10 +225,35 @@ def run_reference(args, rank, world):
         "gpu_launches": 0,
         "note": "rio-rs is Rust; no cargo/rustc in this image, so this is the C++ restatement oracle/directory_model.cpp of local.rs + service.rs:193-254",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries ONE JSON line.  Libraries print there too (NCCL's version banner when the box sets NCCL_DEBUG, nvcc
+    notes, torch warnings), so file descriptor 1 is pointed at stderr for the rest of the run and the line is written to
+    the original stdout at the end."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -257,8 +282,6 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
-        # stdout carries ONE JSON line: when the box sets NCCL_DEBUG (even just VERSION) NCCL's banner would land there
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -418,7 +441,7 @@ def main():
             "clocks": clk,
             "extra_configs": extra,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist:
         dist.barrier()
         dist.destroy_process_group()
