@@ -98,3 +98,22 @@ def test_server_product_does_not_use_the_client_library():
         assert "librio_client" not in src and "rio_client" not in src and "from .client" not in src and "import client" not in src, f
     eng = "".join(open(os.path.join(ROOT, "rio_rs_b200", "csrc", f)).read() for f in ("engine.cu", "resolver.cu"))
     assert "rio_client" not in eng
+
+
+def test_cpp_mirror_conformance(tmp_path):
+    """rio_rs_b200/host/first_hop.hpp (the C++ mirror of the client piece) against oracle-made expectations."""
+    import subprocess
+
+    CL.lib()
+    addrs, seeds, w = O.synth_nodes(40)
+    ids = [("Obj", str(i)) for i in range(400)]
+    keys = np.array([O.object_key(t, i) for t, i in ids], dtype=np.uint64)
+    want = O.assign_hrw(keys, seeds, w)
+    (tmp_path / "nodes.txt").write_text("".join("%s %d\n" % (a, x) for a, x in zip(addrs, w)))
+    (tmp_path / "ids.txt").write_text("".join("%s %s %s\n" % (t, i, addrs[j]) for (t, i), j in zip(ids, want)))
+    exe = str(tmp_path / "first_hop_conformance")
+    libdir = os.path.join(ROOT, "rio_rs_b200")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-o", exe, os.path.join(ROOT, "tests", "cpp", "first_hop_conformance.cpp"),
+                           "-L" + libdir, "-lrio_client", "-Wl,-rpath," + libdir])
+    r = subprocess.run([exe, str(tmp_path / "nodes.txt"), str(tmp_path / "ids.txt")], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "all passed" in r.stdout, r.stdout + r.stderr
