@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define RIO_ABI_VERSION 1
+#define RIO_ABI_VERSION 2
 
 typedef int32_t rio_status;
 #define RIO_OK            0
@@ -97,6 +97,21 @@ rio_status  rio_cuda_node_intern(rio_placement *h, const char *address, uint32_t
 rio_status  rio_cuda_node_address(rio_placement *h, uint32_t idx, char *buf, size_t cap, size_t *out_len);
 rio_status  rio_cuda_node_count(rio_placement *h, uint32_t *out_total, uint32_t *out_live);
 
+/* ---- solver policy of the handle (new; no reference counterpart) ----------------------------------------------------
+ * RIO_SOLVER_HRW  = flat weighted rendezvous over all live nodes: M pair hashes per object, minimal movement
+ *                   on a membership change.  The default.
+ * RIO_SOLVER_HRW2 = hierarchical weighted rendezvous with fan-out 2: the live nodes sit in a binary trie
+ *                   over a hash of their address, every trie node is a 2-way weighted rendezvous between its subtrees decided
+ *                   in closed form (one 31-bit hash of (object, level) against floor(2^31 W_left / (W_left + W_right))), so an
+ *                   object costs trie_bits + O(1) contests instead of M pair hashes; P(node) = w/W as before, movement on a
+ *                   membership change is about (1 + log2(M)/2) x minimal.  trie_bits in [1, 14]; 0 keeps the current depth
+ *                   (default 12).
+ * The policy applies to assign_batch(_dev), the resident-set calls and rebalance; place_batch carries its own policy. */
+#define RIO_SOLVER_HRW  1u
+#define RIO_SOLVER_HRW2 2u
+rio_status  rio_cuda_set_solver(rio_placement *h, uint32_t solver, uint32_t trie_bits);
+rio_status  rio_cuda_get_solver(rio_placement *h, uint32_t *solver, uint32_t *trie_bits);
+
 /* ---- directory: batched LocalObjectPlacement (local.rs:22-68) ------------------------------------------- */
 /* lookup (local.rs:42-49): out_idx[i] = node index or RIO_NONE */
 rio_status  rio_cuda_lookup_batch(rio_placement *h, const uint64_t *keys, size_t n, uint32_t *out_idx);
@@ -117,14 +132,17 @@ rio_status  rio_cuda_assign_batch(rio_placement *h, const uint64_t *keys, const 
                                   uint32_t *out_idx);
 /* Service::get_or_create_placement for a batch (service.rs:193-254): existing & live => keep; recorded on an
  * inactive node => clean_server(that node) then re-place; none => place.  policy RIO_PLACE_SELF re-places on
- * self_idx (the reference's rule, service.rs:244-252); RIO_PLACE_HRW re-places by the solver. */
+ * self_idx (the reference's rule, service.rs:244-252); RIO_PLACE_HRW / RIO_PLACE_HRW2 re-place by the solver. */
 #define RIO_PLACE_SELF 0u
 #define RIO_PLACE_HRW  1u
+#define RIO_PLACE_HRW2 2u   /* re-place by the hierarchical solver (RIO_SOLVER_HRW2 semantics, the handle's trie_bits) */
 rio_status  rio_cuda_place_batch(rio_placement *h, const uint64_t *keys, size_t n, uint32_t policy,
                                  uint32_t self_idx, uint32_t *out_idx);
 /* Eager re-placement of the whole directory after a membership change (replaces the lazy per-object path
  * service.rs:224-238 / 286-297): RIO_EV_JOIN(idx) moves onto idx exactly the objects that now prefer it;
- * RIO_EV_LEAVE(idx) re-places exactly the objects recorded on idx.  out_moved may be NULL. */
+ * RIO_EV_LEAVE(idx) re-places exactly the objects recorded on idx.  Under RIO_SOLVER_HRW2 every placed key is walked
+ * again and the ones whose node changed are rewritten (the state after the call is the fresh assignment over the
+ * live set).  out_moved may be NULL. */
 #define RIO_EV_JOIN  1u
 #define RIO_EV_LEAVE 2u
 rio_status  rio_cuda_rebalance(rio_placement *h, uint32_t event, uint32_t idx, uint64_t *out_moved);

@@ -69,6 +69,18 @@ def lib():
         L.orc_assign_bounded.argtypes = [u64p, C.c_size_t, u64p, u32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u32p, u32p, C.c_int]
         L.orc_assign_affinity.restype = None
         L.orc_assign_affinity.argtypes = [f32p, f32p, u32p, C.c_size_t, C.c_uint32, C.c_uint32, u32p, f64p, f64p, C.c_int]
+        L.orc_assign_hrw2.restype = None
+        L.orc_assign_hrw2.argtypes = [u64p, C.c_size_t, u64p, u32p, u32p, C.c_uint32, C.c_uint32, u32p, C.c_int]
+        L.orc_assign_bounded_hrw2.restype = C.c_uint32
+        L.orc_assign_bounded_hrw2.argtypes = [u64p, C.c_size_t, u64p, u32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u32p, u32p, C.c_int]
+        L.orc_hrw2_v.restype = C.c_uint32
+        L.orc_hrw2_v.argtypes = [C.c_uint64, C.c_uint64]
+        L.orc_hrw2_pos.restype = C.c_uint64
+        L.orc_hrw2_pos.argtypes = [C.c_uint64]
+        L.orc_hrw2_level_seed.restype = C.c_uint64
+        L.orc_hrw2_level_seed.argtypes = [C.c_uint32]
+        L.orc_hrw2_threshold.restype = C.c_uint32
+        L.orc_hrw2_threshold.argtypes = [C.c_uint64, C.c_uint64]
         L.orc_synth_keys.restype = None
         L.orc_synth_keys.argtypes = [u64p, C.c_size_t, C.c_uint64, C.c_uint64]
         L.orc_counts.restype = None
@@ -121,6 +133,23 @@ def assign_hrw(keys, seeds, weights, mask=None, threads=1, want_score=False):
     return (idx, sc, uu) if want_score else idx
 
 
+HRW2_DEFAULT_BITS = 12
+
+
+def assign_hrw2(keys, seeds, weights, mask=None, bits=HRW2_DEFAULT_BITS, threads=1):
+    """Hierarchical weighted rendezvous with fan-out 2."""
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+    weights = np.ascontiguousarray(weights, dtype=np.uint32)
+    n, M = len(keys), len(seeds)
+    idx = np.empty(n, dtype=np.uint32)
+    if mask is not None:
+        mask = np.ascontiguousarray(mask, dtype=np.uint32)
+    lib().orc_assign_hrw2(_p(keys, C.c_uint64), n, _p(seeds, C.c_uint64), _p(weights, C.c_uint32), _p(mask, C.c_uint32), M, bits,
+                          _p(idx, C.c_uint32), threads)
+    return idx
+
+
 def assign_bounded(keys, seeds, weights, cap_num=5, cap_den=4, max_rounds=4, threads=1):
     keys = np.ascontiguousarray(keys, dtype=np.uint64)
     seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
@@ -130,6 +159,18 @@ def assign_bounded(keys, seeds, weights, cap_num=5, cap_den=4, max_rounds=4, thr
     counts = np.zeros(M, dtype=np.uint32)
     passes = lib().orc_assign_bounded(_p(keys, C.c_uint64), n, _p(seeds, C.c_uint64), _p(weights, C.c_uint32), M, cap_num, cap_den,
                                       max_rounds, _p(idx, C.c_uint32), _p(counts, C.c_uint32), threads)
+    return idx, counts, passes
+
+
+def assign_bounded_hrw2(keys, seeds, weights, cap_num=5, cap_den=4, max_rounds=4, bits=HRW2_DEFAULT_BITS, threads=1):
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+    weights = np.ascontiguousarray(weights, dtype=np.uint32)
+    n, M = len(keys), len(seeds)
+    idx = np.empty(n, dtype=np.uint32)
+    counts = np.zeros(M, dtype=np.uint32)
+    passes = lib().orc_assign_bounded_hrw2(_p(keys, C.c_uint64), n, _p(seeds, C.c_uint64), _p(weights, C.c_uint32), M, bits, cap_num,
+                                           cap_den, max_rounds, _p(idx, C.c_uint32), _p(counts, C.c_uint32), threads)
     return idx, counts, passes
 
 

@@ -280,3 +280,129 @@ void orc_counts(const uint32_t *idx, size_t n, uint32_t M, uint32_t *out_counts)
     memset(out_counts, 0, 4 * (size_t)M);
     for (size_t i = 0; i < n; i++) if (idx[i] < M) out_counts[idx[i]]++;
 }
+
+/* ---- 3.8 HRW2: hierarchical weighted rendezvous with fan-out 2 ("rendezvous trie") ----------------------------
+ * Spec, restated here from the text, NOT from the CUDA host code (which precomputes a heap of
+ * thresholds; this file re-derives every contest from prefix sums of the members sorted by position):
+ *   pos(j)   = mix64(seed_j ^ SALT_POS);  bucket(j) = pos(j) >> (64 - bits)   (0 when bits == 0)
+ *   v(key, s) = (p*m + (s2 & 0x7FFFFFFF)) mod 2^31 with p = (lo32(s)*b + ab) mod 2^32, m = hi32(s)|1, s2 = lo32(mix64(s ^ SALT_NODE2)),
+ *               (b, ab) the object's hashed pair of 3.3 -- the flat pair hash reduced to 31 bits
+ *   level l  acts as a pseudo-node with seed c_l = mix64(GOLDEN64*(l+1) ^ SALT_LVL)
+ *   contest(key, s, WL, WR): T = floor(2^31 * WL / (WL + WR));  LEFT iff v(key, s) < T      (s = c_l on trie level l)
+ *     -- the closed form of a 2-way weighted rendezvous between two subtrees: P(LEFT) = WL/(WL+WR) (+-2^-31)
+ *   levels 0..bits-1 walk the binary trie over bucket ids, most significant bit first (LEFT = bit 0);
+ *   inside the bucket the live members sorted by (pos, index) are m_0..m_{c-1}: for k = 0..c-2 the contest "m_k against
+ *     the rest" is keyed by the member's own seed: contest(key, seed(m_k), w_k, sum_{i>k} w_i) LEFT
+ *     takes m_k; nobody took -> m_{c-1}.  (Keyed by the member, not by its rank, so a member's hash survives others leaving.)
+ *   weight 0 / masked nodes are not members.  No live member -> NONE. */
+#define SALT_POS 0x8CB92BA72F3D8DD7ull
+#define SALT_LVL 0x3C79AC492BA7B653ull
+
+uint64_t orc_hrw2_pos(uint64_t seed) { return orc_mix64(seed ^ SALT_POS); }
+uint64_t orc_hrw2_level_seed(uint32_t level) { return orc_mix64(GOLDEN64 * ((uint64_t)level + 1) ^ SALT_LVL); }
+uint32_t orc_hrw2_threshold(uint64_t wl, uint64_t wr) {
+    if (wl + wr == 0) return 0;
+    return (uint32_t)((((unsigned __int128)wl) << 31) / (wl + wr));   /* <= 2^31 */
+}
+
+typedef struct { uint64_t pos, seed; uint32_t j, w; } h2_member;
+static int h2_cmp(const void *a, const void *b) {
+    const h2_member *x = (const h2_member *)a, *y = (const h2_member *)b;
+    if (x->pos != y->pos) return x->pos < y->pos ? -1 : 1;
+    return x->j < y->j ? -1 : (x->j > y->j);
+}
+typedef struct { const uint64_t *keys; const h2_member *mem; const uint64_t *pre; /* pre[i] = sum of w of mem[0..i) */
+                 uint32_t c, bits; uint32_t *out_idx; } h2_ctx;
+
+/* 31-bit contest hash of (key, seed): same multiply-add form as the flat pair hash, reduced mod 2^31 */
+uint32_t orc_hrw2_v(uint64_t key, uint64_t seed) {
+    orc_objh o = obj_hash(key);
+    uint32_t p = (uint32_t)seed * o.b + o.ab;
+    uint32_t s2 = (uint32_t)orc_mix64(seed ^ SALT_NODE2);
+    return (p * ((uint32_t)(seed >> 32) | 1u) + (s2 & 0x7FFFFFFFu)) & 0x7FFFFFFFu;
+}
+static inline int h2_left(uint64_t key, uint64_t contest_seed, uint64_t wl, uint64_t wr) {
+    return orc_hrw2_v(key, contest_seed) < orc_hrw2_threshold(wl, wr);
+}
+/* first member in [lo,hi) whose pos has bit `bit` (counted from the top, 0 = MSB) set; members are sorted by pos and
+ * share the bits above, so this is the split point of the subtree */
+static uint32_t h2_split(const h2_member *mem, uint32_t lo, uint32_t hi, uint32_t bit) {
+    while (lo < hi) { uint32_t mid = lo + (hi - lo) / 2; if ((mem[mid].pos >> (63 - bit)) & 1u) hi = mid; else lo = mid + 1; }
+    return lo;
+}
+static void h2_range(void *p, size_t a, size_t b) {
+    h2_ctx *c = (h2_ctx *)p;
+    for (size_t i = a; i < b; i++) {
+        uint32_t lo = 0, hi = c->c;
+        if (!hi) { c->out_idx[i] = ORC_NONE; continue; }
+        const uint64_t key = c->keys[i];
+        for (uint32_t l = 0; l < c->bits; l++) {
+            uint32_t mid = h2_split(c->mem, lo, hi, l);
+            uint64_t wl = c->pre[mid] - c->pre[lo], wr = c->pre[hi] - c->pre[mid];
+            if (h2_left(key, orc_hrw2_level_seed(l), wl, wr)) hi = mid; else lo = mid;
+        }
+        uint32_t k = lo;
+        for (; k + 1 < hi; k++)   /* the member's own pair hash (the flat rendezvous hash of (key, node)) decides "m_k or the rest" */
+            if (h2_left(key, c->mem[k].seed, c->mem[k].w, c->pre[hi] - c->pre[k + 1])) break;
+        c->out_idx[i] = c->mem[k].j;
+    }
+}
+void orc_assign_hrw2(const uint64_t *keys, size_t n, const uint64_t *seed, const uint32_t *weight, const uint32_t *mask,
+                     uint32_t M, uint32_t bits, uint32_t *out_idx, int threads) {
+    h2_member *mem = (h2_member *)malloc(sizeof(h2_member) * (M ? M : 1));
+    uint32_t c = 0;
+    for (uint32_t j = 0; j < M; j++) {
+        if (!weight[j]) continue;
+        if (mask && (mask[j >> 5] >> (j & 31) & 1u)) continue;
+        mem[c].pos = orc_hrw2_pos(seed[j]); mem[c].seed = seed[j]; mem[c].j = j; mem[c].w = weight[j]; c++;
+    }
+    qsort(mem, c, sizeof(h2_member), h2_cmp);
+    uint64_t *pre = (uint64_t *)malloc(8 * ((size_t)c + 1));
+    pre[0] = 0;
+    for (uint32_t i = 0; i < c; i++) pre[i + 1] = pre[i] + mem[i].w;
+    h2_ctx ctx = { keys, mem, pre, c, bits, out_idx };
+    par_for(n, threads, h2_range, &ctx);
+    free(mem); free(pre);
+}
+
+/* 3.5 bounded-load rounds on top of the HRW2 policy: identical round rule, the assignment passes use orc_assign_hrw2
+ * (closed nodes are simply not members of the trie of the later passes). */
+uint32_t orc_assign_bounded_hrw2(const uint64_t *keys, size_t n, const uint64_t *seed, const uint32_t *weight,
+                                 uint32_t M, uint32_t bits, uint32_t cap_num, uint32_t cap_den, uint32_t max_rounds,
+                                 uint32_t *out_idx, uint32_t *out_counts, int threads) {
+    uint32_t words = (M + 31) / 32;
+    uint32_t *closed = (uint32_t *)calloc(words ? words : 1, 4);
+    uint32_t *cap = (uint32_t *)calloc(M ? M : 1, 4);
+    uint32_t *thr = (uint32_t *)calloc(M ? M : 1, 4);
+    uint8_t *over = (uint8_t *)calloc(M ? M : 1, 1);
+    uint64_t *skeys = (uint64_t *)malloc(8 * (n ? n : 1));
+    uint32_t *spos = (uint32_t *)malloc(4 * (n ? n : 1)), *sidx = (uint32_t *)malloc(4 * (n ? n : 1));
+    uint64_t W = 0;
+    for (uint32_t j = 0; j < M; j++) W += weight[j];
+    for (uint32_t j = 0; j < M; j++) cap[j] = orc_capacity(n, weight[j], W, cap_num, cap_den);
+    orc_assign_hrw2(keys, n, seed, weight, NULL, M, bits, out_idx, threads);
+    uint32_t passes = 1;
+    for (uint32_t r = 1; r < max_rounds; r++) {
+        orc_counts(out_idx, n, M, out_counts);
+        int any = 0; uint32_t open = 0;
+        for (uint32_t j = 0; j < M; j++) {
+            over[j] = weight[j] && out_counts[j] > cap[j];
+            if (over[j]) { any = 1; closed[j >> 5] |= 1u << (j & 31);
+                thr[j] = (uint32_t)((((uint64_t)(out_counts[j] - cap[j])) << 32) / out_counts[j]); }
+        }
+        for (uint32_t j = 0; j < M; j++) if (weight[j] && !(closed[j >> 5] >> (j & 31) & 1u)) open++;
+        if (!any || !open) break;
+        size_t ns = 0;
+        for (size_t i = 0; i < n; i++) {
+            uint32_t j = out_idx[i];
+            if (j == ORC_NONE || !over[j]) continue;
+            if (orc_spill_hash(keys[i], r) < thr[j]) { skeys[ns] = keys[i]; spos[ns] = (uint32_t)i; ns++; }
+        }
+        orc_assign_hrw2(skeys, ns, seed, weight, closed, M, bits, sidx, threads);
+        for (size_t q = 0; q < ns; q++) out_idx[spos[q]] = sidx[q];
+        passes++;
+    }
+    orc_counts(out_idx, n, M, out_counts);
+    free(closed); free(cap); free(thr); free(over); free(skeys); free(spos); free(sidx);
+    return passes;
+}

@@ -5,7 +5,8 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 NONE = 0xFFFFFFFF
 RIO_OK, RIO_ERR_UPSTREAM, RIO_ERR_UNKNOWN = 0, -1, -2
-PLACE_SELF, PLACE_HRW = 0, 1
+PLACE_SELF, PLACE_HRW, PLACE_HRW2 = 0, 1, 2
+SOLVER_HRW, SOLVER_HRW2 = 1, 2
 EV_JOIN, EV_LEAVE = 1, 2
 COMM_ID_BYTES = 128
 
@@ -48,6 +49,8 @@ SIGNATURES = {
     "rio_cuda_node_intern": (C.c_int32, [H, C.c_char_p, u32p]),
     "rio_cuda_node_address": (C.c_int32, [H, C.c_uint32, C.c_char_p, sz, C.POINTER(sz)]),
     "rio_cuda_node_count": (C.c_int32, [H, u32p, u32p]),
+    "rio_cuda_set_solver": (C.c_int32, [H, C.c_uint32, C.c_uint32]),
+    "rio_cuda_get_solver": (C.c_int32, [H, u32p, u32p]),
     "rio_cuda_lookup_batch": (C.c_int32, [H, vp, sz, vp]),
     "rio_cuda_upsert_batch": (C.c_int32, [H, vp, vp, sz]),
     "rio_cuda_remove_batch": (C.c_int32, [H, vp, sz]),

@@ -109,8 +109,9 @@ struct NodeInfo {
 };
 
 struct TabBufs {
-    DevBuf recs, classes, by_idx;
+    DevBuf recs, classes, by_idx, trie_blob;
     NodeTabDev tab{};
+    TrieDev trie{};
 };
 
 // device scalars (one small allocation): [0]=nsel [1]=moved/removed [2]=new keys (cumulative) [3]=placed ; u32 error at [8]
@@ -129,6 +130,8 @@ struct rio_placement {
     std::vector<NodeInfo> nodes;
     std::unordered_map<std::string, uint32_t> node_index;
     uint32_t K = 0;
+    uint32_t solver = RIO_SOLVER_HRW;   // policy of assign_batch / set_assign / rebalance (rio_cuda_set_solver)
+    uint32_t trie_bits = 12;            // HRW2: depth of the binary trie over node positions
     bool tab_dirty = true;
     TabBufs tabs, tabs_masked;
     DevBuf d_node_state, d_live, d_fnode, d_fnode_c, d_fnode_g, d_nidx_map;
@@ -235,7 +238,46 @@ void build_tab(rio_placement *h, TabBufs &tb, const std::vector<uint8_t> *closed
         const bool lv = ni.live() && !(closed && (*closed)[j]);
         by_idx[j] = make_uint4((uint32_t)ni.seed, lv ? inv_weight(ni.weight) : 0u, (uint32_t)(ni.seed >> 32) | 1u, (uint32_t)ni.seed2);
     }
+    // ---- HRW2 table: thresholds of the binary trie over node positions, leaf words, chain records ----
+    const uint32_t bits = h->trie_bits, nb = 1u << bits;
+    struct Mem { uint64_t pos; uint32_t idx, w; };
+    std::vector<Mem> mem;
+    mem.reserve(live.size());
+    for (const Ent &e : live) mem.push_back(Mem{mix64(h->nodes[e.idx].seed ^ kSaltPos), e.idx, h->nodes[e.idx].weight});
+    std::sort(mem.begin(), mem.end(), [](const Mem &a, const Mem &b) { return a.pos != b.pos ? a.pos < b.pos : a.idx < b.idx; });
+    std::vector<uint64_t> wsum((size_t)2 * nb, 0);                 // heap of subtree weights, leaves at [nb, 2nb)
+    std::vector<uint32_t> bstart((size_t)nb + 1, 0);
+    for (const Mem &m : mem) { const uint32_t bk = bits ? (uint32_t)(m.pos >> (64 - bits)) : 0u; wsum[nb + bk] += m.w; bstart[bk + 1]++; }
+    for (uint32_t k = 0; k < nb; k++) bstart[k + 1] += bstart[k];
+    for (uint32_t i = nb - 1; i >= 1; i--) wsum[i] = wsum[2 * i] + wsum[2 * i + 1];
+    std::vector<uint32_t> tab32((size_t)2 * nb, 0);
+    for (uint32_t i = 1; i < nb; i++) tab32[i] = contest_t3(wsum[2 * i], wsum[2 * i + 1]);
+    std::vector<uint4> crec;
+    std::vector<uint32_t> cnidx;
+    for (uint32_t k = 0; k < nb; k++) {
+        const uint32_t lo = bstart[k], hi = bstart[k + 1];
+        if (lo == hi) { tab32[nb + k] = kNone; continue; }
+        if (hi - lo == 1) { tab32[nb + k] = mem[lo].idx; continue; }
+        tab32[nb + k] = 0x80000000u | (uint32_t)crec.size();
+        uint64_t rest = wsum[nb + k];
+        for (uint32_t q = lo; q < hi; q++) {
+            rest -= mem[q].w;
+            const ContestRec r = contest_rec(h->nodes[mem[q].idx].seed);
+            crec.push_back(make_uint4(r.s0, r.m2, r.h2, q + 1 == hi ? 0xFFFFFFFFu : contest_t3(mem[q].w, rest)));
+            cnidx.push_back(mem[q].idx);
+        }
+    }
+    const uint32_t off_crec = (uint32_t)((tab32.size() * 4 + 15) / 16 * 16);
+    const uint32_t off_cnidx = off_crec + (uint32_t)crec.size() * 16;
+    const uint32_t blob_bytes = (uint32_t)((off_cnidx + cnidx.size() * 4 + 15) / 16 * 16);
+    std::vector<unsigned char> blob(blob_bytes ? blob_bytes : 16, 0);
+    memcpy(blob.data(), tab32.data(), tab32.size() * 4);
+    if (!crec.empty()) { memcpy(blob.data() + off_crec, crec.data(), crec.size() * 16); memcpy(blob.data() + off_cnidx, cnidx.data(), cnidx.size() * 4); }
+
     cudaStream_t st = h->stream;
+    tb.trie_blob.ensure(blob.size(), st);
+    CUDA_TRY(cudaMemcpyAsync(tb.trie_blob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, st));
+    tb.trie = TrieDev{tb.trie_blob.p, (uint32_t)blob.size(), off_crec, off_cnidx, bits, (uint32_t)crec.size()};
     tb.recs.ensure(recs.size() * sizeof(NodeRec), st);
     tb.classes.ensure(classes.size() * sizeof(ClassRec), st);
     tb.by_idx.ensure(by_idx.size() * sizeof(uint4), st);
@@ -363,6 +405,13 @@ void exchange_counters(rio_placement *h, const uint32_t *d_local, uint32_t *d_gl
     launch_sum_gathered(h->L(), h->s_gather.as<uint32_t>(), (uint32_t)h->world, M, d_global);
 }
 
+// the hash-path solver of the handle: flat weighted rendezvous (M pair hashes per object) or HRW2 (~log2 M contests)
+void run_assign(rio_placement *h, uint32_t solver, const TabBufs &tb, const uint64_t *d_keys, uint64_t n, uint32_t *d_out_idx, uint32_t *d_counters,
+                const uint32_t *d_sel, uint64_t n_sel) {
+    if (solver == RIO_SOLVER_HRW2) launch_assign_trie(h->L(), d_keys, n, tb.trie, d_out_idx, d_counters, d_sel, n_sel, tb.tab.n_total);
+    else launch_assign_hrw(h->L(), d_keys, n, tb.tab, d_out_idx, d_counters, d_sel, n_sel);
+}
+
 // affinity dispatch: tcgen05 kernel for K == 16 (unless RIO_AFFINITY_VARIANT=ffma or the node set does not fit), else CUDA cores
 void run_affinity(rio_placement *h, const float *d_fobj, uint64_t n, uint32_t *d_out_idx, float *d_out_cost, uint32_t *d_counters) {
     if (!n) return;
@@ -390,8 +439,9 @@ void assign_host_pipelined(rio_placement *h, const uint64_t *keys, const float *
     if (feats) REQUIRE(h->K > 0, "assign with object features needs node features (set_nodes feats)");
     // chunks of two full kernel waves (about 0.9 M objects on 148 SMs): whole waves leave no tail, small chunks keep the
     // pipeline fill/drain (first H2D, last D2H) short
-    const size_t chunk = feats ? (size_t)(1u << 20) : (size_t)(2 * assign_wave_objects(h->sm_count));
-    h->s_keys.ensure(n * 8, h->stream);
+    const size_t chunk = feats ? (size_t)(1u << 20)
+                               : (h->solver == RIO_SOLVER_HRW2 ? (size_t)(4 * trie_wave_objects(h->sm_count)) : (size_t)(2 * assign_wave_objects(h->sm_count)));
+    if (!feats) h->s_keys.ensure(n * 8, h->stream);
     h->s_idx.ensure(n * 4, h->stream);
     if (feats) h->s_feats.ensure(n * (size_t)h->K * 4, h->stream);
     CUDA_TRY(cudaEventRecord(h->ev_pipe[0], h->stream));          // buffers (re)allocated on the main stream
@@ -399,14 +449,14 @@ void assign_host_pipelined(rio_placement *h, const uint64_t *keys, const float *
     CUDA_TRY(cudaStreamWaitEvent(h->d2h_stream, h->ev_pipe[0], 0));
     for (size_t lo = 0; lo < n; lo += chunk) {
         const size_t m = std::min(chunk, n - lo);
-        CUDA_TRY(cudaMemcpyAsync(h->s_keys.as<uint64_t>() + lo, keys + lo, m * 8, cudaMemcpyHostToDevice, h->h2d_stream));
+        if (!feats) CUDA_TRY(cudaMemcpyAsync(h->s_keys.as<uint64_t>() + lo, keys + lo, m * 8, cudaMemcpyHostToDevice, h->h2d_stream));   // keys may be NULL with feats
         if (feats) CUDA_TRY(cudaMemcpyAsync(h->s_feats.as<float>() + lo * h->K, feats + lo * h->K, m * (size_t)h->K * 4, cudaMemcpyHostToDevice, h->h2d_stream));
         CUDA_TRY(cudaEventRecord(h->ev_pipe[1], h->h2d_stream));
         CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_pipe[1], 0));
         if (feats)
             run_affinity(h, h->s_feats.as<float>() + lo * h->K, m, h->s_idx.as<uint32_t>() + lo, nullptr, nullptr);
         else
-            launch_assign_hrw(h->L(), h->s_keys.as<uint64_t>() + lo, m, h->tabs.tab, h->s_idx.as<uint32_t>() + lo, nullptr, nullptr, 0);
+            run_assign(h, h->solver, h->tabs, h->s_keys.as<uint64_t>() + lo, m, h->s_idx.as<uint32_t>() + lo, nullptr, nullptr, 0);
         CUDA_TRY(cudaEventRecord(h->ev_pipe[2], h->stream));
         CUDA_TRY(cudaStreamWaitEvent(h->d2h_stream, h->ev_pipe[2], 0));
         CUDA_TRY(cudaMemcpyAsync(out + lo, h->s_idx.as<uint32_t>() + lo, m * 4, cudaMemcpyDeviceToHost, h->d2h_stream));
@@ -423,6 +473,9 @@ rio_status guarded(rio_placement *h, F &&f) {
             std::lock_guard<std::mutex> g(h->mu);
             use_device(h);
             f();
+            // a failed launch (bad configuration, wrong architecture) is not reported by the later synchronize/memcpy calls
+            const cudaError_t le = cudaGetLastError();
+            if (le != cudaSuccess) throw RioError{RIO_ERR_UPSTREAM, std::string("kernel launch failed: ") + cudaGetErrorString(le)};
         } else {
             f();
         }
@@ -483,6 +536,8 @@ rio_status rio_cuda_create(const rio_config *cfg, rio_placement **out) {
         h->sm_count = prop.multiProcessorCount;
         h->hbm = prop.totalGlobalMem;
         h->devname = prop.name;
+        trie_upload_level_constants(dev);
+        CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
@@ -526,7 +581,7 @@ void rio_cuda_destroy(rio_placement *h) {
             if (h->xchg_ready && p != h->rank && h->xchg_peer[p]) cudaIpcCloseMemHandle(h->xchg_peer[p]);
         cudaFree(h->xchg_mine);
     }
-    DevBuf *bufs[] = {&h->tabs.recs, &h->tabs.classes, &h->tabs.by_idx, &h->tabs_masked.recs, &h->tabs_masked.classes, &h->tabs_masked.by_idx,
+    DevBuf *bufs[] = {&h->tabs.recs, &h->tabs.classes, &h->tabs.by_idx, &h->tabs_masked.recs, &h->tabs_masked.classes, &h->tabs_masked.by_idx, &h->tabs.trie_blob, &h->tabs_masked.trie_blob,
                       &h->d_node_state, &h->d_live, &h->d_fnode, &h->d_fnode_c, &h->d_fnode_g, &h->d_nidx_map, &h->s_keys, &h->s_idx, &h->s_idx2, &h->s_sel, &h->s_slots, &h->s_keys2, &h->s_feats,
                       &h->s_packed, &h->s_offsets, &h->s_cost, &h->s_misc, &h->s_flush, &h->s_gather};
     for (DevBuf *b : bufs) b->release(h->stream);
@@ -664,6 +719,21 @@ rio_status rio_cuda_node_count(rio_placement *h, uint32_t *out_total, uint32_t *
     });
 }
 
+rio_status rio_cuda_set_solver(rio_placement *h, uint32_t solver, uint32_t trie_bits) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] {
+        REQUIRE(solver == RIO_SOLVER_HRW || solver == RIO_SOLVER_HRW2, "unknown solver");
+        REQUIRE(trie_bits <= 14, "trie_bits must be in [0, 14] (0 = keep the current depth)");
+        h->solver = solver;
+        if (trie_bits && trie_bits != h->trie_bits) { h->trie_bits = trie_bits; h->tab_dirty = true; }
+    });
+}
+
+rio_status rio_cuda_get_solver(rio_placement *h, uint32_t *solver, uint32_t *trie_bits) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] { if (solver) *solver = h->solver; if (trie_bits) *trie_bits = h->trie_bits; });
+}
+
 // ---- directory -----------------------------------------------------------------------------------------------------
 rio_status rio_cuda_lookup_batch(rio_placement *h, const uint64_t *keys, size_t n, uint32_t *out_idx) {
     if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
@@ -758,8 +828,7 @@ rio_status rio_cuda_assign_batch(rio_placement *h, const uint64_t *keys, const f
         if (!n) return;
         REQUIRE((keys || obj_feats) && out_idx, "null buffer");
         if (!obj_feats) REQUIRE(keys, "keys is NULL");
-        static const uint64_t dummy = 0;
-        assign_host_pipelined(h, keys ? keys : &dummy, obj_feats, n, out_idx);
+        assign_host_pipelined(h, keys, obj_feats, n, out_idx);
     });
 }
 
@@ -773,7 +842,7 @@ rio_status rio_cuda_assign_batch_dev(rio_placement *h, const uint64_t *d_keys, c
             REQUIRE(h->K > 0, "assign with object features needs node features");
             run_affinity(h, d_obj_feats, n, d_out_idx, nullptr, nullptr);
         } else {
-            launch_assign_hrw(h->L(), d_keys, n, h->tabs.tab, d_out_idx, nullptr, nullptr, 0);
+            run_assign(h, h->solver, h->tabs, d_keys, n, d_out_idx, nullptr, nullptr, 0);
         }
     });
 }
@@ -799,7 +868,7 @@ rio_status rio_cuda_place_batch(rio_placement *h, const uint64_t *keys, size_t n
     return guarded(h, [&] {
         if (!n) return;
         REQUIRE(keys && out_idx, "null buffer");
-        REQUIRE(policy == RIO_PLACE_SELF || policy == RIO_PLACE_HRW, "unknown policy");
+        REQUIRE(policy == RIO_PLACE_SELF || policy == RIO_PLACE_HRW || policy == RIO_PLACE_HRW2, "unknown policy");
         REQUIRE(n < 0xFFFFFFFFull, "batch too large");
         if (policy == RIO_PLACE_SELF) REQUIRE(self_idx < h->nodes.size(), "self_idx is not a known node");
         ensure_tab(h);
@@ -821,7 +890,7 @@ rio_status rio_cuda_place_batch(rio_placement *h, const uint64_t *keys, size_t n
             zero_scalar(h, S_MOVED);
             launch_dir_clean_flagged(h->L(), h->dir, h->s_misc.as<uint8_t>(), n_total, h->d_scalars + S_MOVED);
             if (policy == RIO_PLACE_SELF) launch_scatter_const(h->L(), h->s_idx.as<uint32_t>(), h->s_sel.as<uint32_t>(), nsel, self_idx);   // :244-252
-            else launch_assign_hrw(h->L(), h->s_keys.as<uint64_t>(), n, h->tabs.tab, h->s_idx.as<uint32_t>(), nullptr, h->s_sel.as<uint32_t>(), nsel);
+            else run_assign(h, policy == RIO_PLACE_HRW2 ? RIO_SOLVER_HRW2 : RIO_SOLVER_HRW, h->tabs, h->s_keys.as<uint64_t>(), n, h->s_idx.as<uint32_t>(), nullptr, h->s_sel.as<uint32_t>(), nsel);
             h->s_keys2.ensure(nsel * 8, st);
             h->s_idx2.ensure(nsel * 4, st);
             launch_gather_keys(h->L(), h->s_keys.as<uint64_t>(), h->s_sel.as<uint32_t>(), nsel, h->s_keys2.as<uint64_t>(), h->s_idx.as<uint32_t>(),
@@ -841,13 +910,12 @@ rio_status rio_cuda_rebalance(rio_placement *h, uint32_t event, uint32_t idx, ui
         REQUIRE(idx < h->nodes.size(), "node index out of range");
         ensure_tab(h);
         zero_scalar(h, S_MOVED);
-        if (event == RIO_EV_JOIN) {
-            REQUIRE(h->nodes[idx].live(), "JOIN of a node that is not live");
-            launch_dir_rebalance_join(h->L(), h->dir, h->tabs.tab, idx, h->d_scalars + S_MOVED);
-        } else {
-            REQUIRE(!h->nodes[idx].live(), "LEAVE of a node that is still live (deactivate it first)");
-            launch_dir_rebalance_leave(h->L(), h->dir, h->tabs.tab, idx, h->d_scalars + S_MOVED);
-        }
+        if (event == RIO_EV_JOIN) REQUIRE(h->nodes[idx].live(), "JOIN of a node that is not live");
+        else REQUIRE(!h->nodes[idx].live(), "LEAVE of a node that is still live (deactivate it first)");
+        if (h->solver == RIO_SOLVER_HRW2)   // thresholds changed on the whole root path of the node: every placed key is walked again (16 B/slot stream)
+            launch_dir_reassign_trie(h->L(), h->dir, h->tabs.trie, h->d_scalars + S_MOVED);
+        else if (event == RIO_EV_JOIN) launch_dir_rebalance_join(h->L(), h->dir, h->tabs.tab, idx, h->d_scalars + S_MOVED);
+        else launch_dir_rebalance_leave(h->L(), h->dir, h->tabs.tab, idx, h->d_scalars + S_MOVED);
         const uint64_t m = read_scalar(h, S_MOVED);
         if (out_moved) *out_moved = m;
     });
@@ -929,7 +997,7 @@ rio_status rio_cuda_set_assign(rio_objset *s, uint32_t use_affinity) {
             REQUIRE(s->K > 0 && s->K == h->K, "set features / node features missing or of different K");
             run_affinity(h, s->feats.as<float>(), s->n, s->idx.as<uint32_t>(), nullptr, s->counters.as<uint32_t>());
         } else {
-            launch_assign_hrw(h->L(), s->keys.as<uint64_t>(), s->n, h->tabs.tab, s->idx.as<uint32_t>(), s->counters.as<uint32_t>(), nullptr, 0);
+            run_assign(h, h->solver, h->tabs, s->keys.as<uint64_t>(), s->n, s->idx.as<uint32_t>(), s->counters.as<uint32_t>(), nullptr, 0);
         }
         s->assigned = true;
     });
@@ -955,7 +1023,7 @@ rio_status rio_cuda_set_assign_bounded(rio_objset *s, uint64_t n_total_objs, uin
         uint32_t *d_thr = d_glob + M;
         uint8_t *d_over = reinterpret_cast<uint8_t *>(d_thr + M);
         CUDA_TRY(cudaMemsetAsync(s->counters.p, 0, (size_t)std::max(M, 1u) * 4, st));
-        launch_assign_hrw(h->L(), s->keys.as<uint64_t>(), s->n, h->tabs.tab, s->idx.as<uint32_t>(), s->counters.as<uint32_t>(), nullptr, 0);
+        run_assign(h, h->solver, h->tabs, s->keys.as<uint64_t>(), s->n, s->idx.as<uint32_t>(), s->counters.as<uint32_t>(), nullptr, 0);
         uint32_t passes = 1;
         for (uint32_t r = 1; r < max_rounds; r++) {
             exchange_counters(h, s->counters.as<uint32_t>(), d_glob, M);                  // the one collective of this pass
@@ -976,7 +1044,7 @@ rio_status rio_cuda_set_assign_bounded(rio_objset *s, uint64_t n_total_objs, uin
                                 s->counters.as<uint32_t>());
             const uint64_t nsel = read_scalar(h, S_NSEL);
             build_tab(h, h->tabs_masked, &closed);
-            if (nsel) launch_assign_hrw(h->L(), s->keys.as<uint64_t>(), s->n, h->tabs_masked.tab, s->idx.as<uint32_t>(), s->counters.as<uint32_t>(), s->sel.as<uint32_t>(), nsel);
+            if (nsel) run_assign(h, h->solver, h->tabs_masked, s->keys.as<uint64_t>(), s->n, s->idx.as<uint32_t>(), s->counters.as<uint32_t>(), s->sel.as<uint32_t>(), nsel);
             passes++;
         }
         s->assigned = true;
@@ -996,7 +1064,14 @@ rio_status rio_cuda_set_rebalance(rio_objset *s, uint32_t event, uint32_t idx, u
         set_ensure_counters(s);
         zero_scalar(h, S_MOVED);
         uint64_t moved = 0;
-        if (event == RIO_EV_JOIN) {
+        if (h->solver == RIO_SOLVER_HRW2) {
+            if (event == RIO_EV_JOIN) REQUIRE(h->nodes[idx].live(), "JOIN of a node that is not live");
+            else REQUIRE(!h->nodes[idx].live(), "LEAVE of a node that is still live (deactivate it first)");
+            // one streaming pass: walk every key again, write only the indices that changed, rebuild the counters
+            CUDA_TRY(cudaMemsetAsync(s->counters.p, 0, (size_t)std::max(s->counters_n, 1u) * 4, h->stream));
+            launch_reassign_trie(h->L(), s->keys.as<uint64_t>(), s->n, h->tabs.trie, s->idx.as<uint32_t>(), s->counters.as<uint32_t>(), h->tabs.tab.n_total, h->d_scalars + S_MOVED);
+            moved = read_scalar(h, S_MOVED);
+        } else if (event == RIO_EV_JOIN) {
             REQUIRE(h->nodes[idx].live(), "JOIN of a node that is not live");
             launch_rebalance_join(h->L(), s->keys.as<uint64_t>(), s->idx.as<uint32_t>(), s->n, h->tabs.tab, idx, s->counters.as<uint32_t>(), h->d_scalars + S_MOVED);
             moved = read_scalar(h, S_MOVED);
@@ -1006,7 +1081,7 @@ rio_status rio_cuda_set_rebalance(rio_objset *s, uint32_t event, uint32_t idx, u
             launch_select_on_node(h->L(), s->idx.as<uint32_t>(), s->n, idx, s->sel.as<uint32_t>(), h->d_scalars + S_NSEL);
             moved = read_scalar(h, S_NSEL);
             CUDA_TRY(cudaMemsetAsync(s->counters.as<uint32_t>() + idx, 0, 4, h->stream));
-            if (moved) launch_assign_hrw(h->L(), s->keys.as<uint64_t>(), s->n, h->tabs.tab, s->idx.as<uint32_t>(), s->counters.as<uint32_t>(), s->sel.as<uint32_t>(), moved);
+            if (moved) run_assign(h, RIO_SOLVER_HRW, h->tabs, s->keys.as<uint64_t>(), s->n, s->idx.as<uint32_t>(), s->counters.as<uint32_t>(), s->sel.as<uint32_t>(), moved);
         }
         if (out_moved) *out_moved = moved;
     });

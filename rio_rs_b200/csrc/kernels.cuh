@@ -28,6 +28,19 @@ struct NodeTabDev {
     const uint4 *by_idx;       // {s0, invw (0 = not live), hi32(seed)|1, s2}
 };
 
+// ---- HRW2 table: one contiguous blob, staged into shared memory by ONE cp.async.bulk ---------
+//   [0, 4 << bits)                 thresholds T3 of the trie nodes, heap order (index 1 = root; [0] unused)
+//   [4 << bits, 8 << bits)         leaf words, one per bucket: node index | 0x80000000 + chain start | kNone (empty)
+//   off_crec  (16-byte aligned)    chain records {s0, m2, h2, T3}: member-keyed contests inside multi-node buckets
+//   off_cnidx                      node index of each chain record
+struct TrieDev {
+    const void *blob;
+    uint32_t blob_bytes;   // multiple of 16
+    uint32_t off_crec, off_cnidx;
+    uint32_t bits;
+    uint32_t n_chain;
+};
+
 // ---- directory: open addressing, 16-byte AoS slots ------------------------------------------------------
 // key == kEmptyKey: free.  val = (seq << 32) | node; seq is non-zero only inside an upsert batch.
 struct __align__(16) DirSlot {
@@ -48,6 +61,9 @@ struct Launch { cudaStream_t stream; int sm_count; uint64_t *launch_counter; };
 void launch_assign_hrw(const Launch &L, const uint64_t *d_keys, uint64_t n, const NodeTabDev &tab, uint32_t *d_out_idx,
                        uint32_t *d_counters /*nullable, n_total entries*/, const uint32_t *d_sel /*nullable*/, uint64_t n_sel);
 uint64_t assign_wave_objects(int sm_count);
+// HRW2 (k_trie.cu)
+void trie_upload_level_constants(int device);
+uint64_t trie_wave_objects(int sm_count);
 void launch_assign_affinity(const Launch &L, const float *d_fobj, uint64_t n, const float *d_fnode /*n_total x K*/,
                             const uint32_t *d_live /*n_total flags*/, uint32_t n_total, uint32_t K, uint32_t *d_out_idx,
                             float *d_out_cost /*nullable*/, uint32_t *d_counters);
@@ -84,6 +100,13 @@ void launch_dir_count(const Launch &L, const DirDev &dir, unsigned long long *d_
 // directory-wide rebalance
 void launch_dir_rebalance_join(const Launch &L, const DirDev &dir, const NodeTabDev &tab, uint32_t new_idx, unsigned long long *d_moved);
 void launch_dir_rebalance_leave(const Launch &L, const DirDev &dir, const NodeTabDev &tab, uint32_t gone_idx, unsigned long long *d_moved);
+
+// HRW2 launchers; DirDev-based one is the directory-wide eager rebalance
+void launch_assign_trie(const Launch &L, const uint64_t *d_keys, uint64_t n, const TrieDev &t, uint32_t *d_out_idx, uint32_t *d_counters /*nullable*/,
+                        const uint32_t *d_sel /*nullable*/, uint64_t n_sel, uint32_t n_total);
+void launch_reassign_trie(const Launch &L, const uint64_t *d_keys, uint64_t n, const TrieDev &t, uint32_t *d_idx, uint32_t *d_counters /*nullable*/,
+                          uint32_t n_total, unsigned long long *d_moved);
+void launch_dir_reassign_trie(const Launch &L, const DirDev &dir, const TrieDev &t, unsigned long long *d_moved);
 
 // place_batch support: classify looked-up placements against node liveness
 // need[i] = 1 if object must be (re)placed; dead_flag[node] = 1 for inactive well-formed nodes that were hit

@@ -72,7 +72,7 @@ static thread_local std::string t_resolver_error;
 extern "C" {
 
 rio_status rio_cuda_resolver_create(rio_placement *h, uint32_t policy, uint32_t self_idx, uint32_t max_batch, uint32_t max_wait_us, rio_resolver **out) {
-    if (!h || !out || (policy != RIO_PLACE_SELF && policy != RIO_PLACE_HRW)) return RIO_ERR_UNKNOWN;
+    if (!h || !out || (policy != RIO_PLACE_SELF && policy != RIO_PLACE_HRW && policy != RIO_PLACE_HRW2)) return RIO_ERR_UNKNOWN;
     rio_resolver *r = new rio_resolver();
     r->h = h; r->policy = policy; r->self_idx = self_idx;
     r->max_batch = max_batch ? max_batch : 4096;

@@ -18,6 +18,8 @@ constexpr uint64_t kSaltObj = 0xD6E8FEB86659FD93ull;
 constexpr uint64_t kSaltNode2 = 0xA0761D6478BD642Full;
 constexpr uint64_t kSaltSpill = 0x2545F4914F6CDD1Dull;
 constexpr uint64_t kGolden64 = 0x9E3779B97F4A7C15ull;
+constexpr uint64_t kSaltPos = 0x8CB92BA72F3D8DD7ull;     // HRW2: node position in the trie
+constexpr uint64_t kSaltLevel = 0x3C79AC492BA7B653ull;   // HRW2: pseudo-node seed of a trie level
 constexpr uint32_t kPairC1 = 0x9E3779B1u;
 constexpr uint32_t kLogK0 = 0x71376877u, kLogK1 = 0x44D58AB6u, kLogK2 = 0x2677DB2Eu, kLogK3 = 0x0B98D5FAu;
 constexpr uint64_t kFnvBasis = 0xCBF29CE484222325ull, kFnvPrime = 0x100000001B3ull;
@@ -77,6 +79,30 @@ RIO_HD ObjHash obj_hash(uint64_t key) {
 RIO_HD uint32_t pair_hash(ObjHash o, uint32_t s0, uint32_t m, uint32_t s2) {
     const uint32_t p = s0 * o.b + o.ab;
     return p * m + s2;
+}
+
+// ---- HRW2: a contest is "v(key, seed) < T", v the pair hash reduced to 31 bits.  The kernels evaluate it
+// as u = p * (2m) + (2h + 1) = 2v + 1 (always odd) against T3 = max(2T - 1, 0): u <= T3  <=>  v < T, for every T in [0, 2^31]
+// -- both forced outcomes (T = 0: never, T = 2^31: always) are representable in one unsigned 32-bit compare.
+struct ContestRec { uint32_t s0, m2, h2; };   // m2 = 2 * (hi32(seed) | 1), h2 = 2 * (s2 & 0x7FFFFFFF) + 1
+RIO_HD ContestRec contest_rec(uint64_t seed) {
+    const uint32_t s2 = (uint32_t)mix64(seed ^ kSaltNode2);
+    ContestRec r;
+    r.s0 = (uint32_t)seed;
+    r.m2 = ((uint32_t)(seed >> 32) | 1u) << 1;
+    r.h2 = (s2 << 1) | 1u;
+    return r;
+}
+RIO_HD uint32_t contest_u(ObjHash o, uint32_t s0, uint32_t m2, uint32_t h2) {
+    const uint32_t p = s0 * o.b + o.ab;
+    return p * m2 + h2;
+}
+inline uint64_t level_seed(uint32_t level) { return mix64(kGolden64 * ((uint64_t)level + 1) ^ kSaltLevel); }
+// T3 of a contest between a left part of weight wl and a right part of weight wr
+inline uint32_t contest_t3(uint64_t wl, uint64_t wr) {
+    if (wl + wr == 0 || wl == 0) return 0u;
+    const uint64_t t = (uint64_t)((((unsigned __int128)wl) << 31) / (wl + wr));   // <= 2^31
+    return t ? (uint32_t)(2 * t - 1) : 0u;
 }
 
 RIO_HD uint32_t inv_weight(uint32_t w) { return w ? 0xFFFFFFFFu / w : 0u; }

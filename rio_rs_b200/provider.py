@@ -216,6 +216,15 @@ class GpuObjectPlacement:
         return out[:total]
 
     # ---- solver ------------------------------------------------------------------------------------------
+    def set_solver(self, solver="hrw", trie_bits=0):
+        """'hrw' = flat weighted rendezvous (default); 'hrw2' = hierarchical, fan-out 2."""
+        self._ck(self.L.rio_cuda_set_solver(self.h, N.SOLVER_HRW2 if solver == "hrw2" else N.SOLVER_HRW, trie_bits))
+
+    def get_solver(self):
+        a, b = C.c_uint32(0), C.c_uint32(0)
+        self._ck(self.L.rio_cuda_get_solver(self.h, C.byref(a), C.byref(b)))
+        return ("hrw2" if a.value == N.SOLVER_HRW2 else "hrw"), b.value
+
     def assign_batch(self, keys=None, obj_feats=None, out=None):
         if obj_feats is not None:
             obj_feats = np.ascontiguousarray(obj_feats, dtype=np.float32)
@@ -231,7 +240,7 @@ class GpuObjectPlacement:
     def place_batch(self, keys, policy="hrw", self_address=None):
         keys = np.ascontiguousarray(keys, dtype=np.uint64)
         out = np.empty(len(keys), dtype=np.uint32)
-        pol = N.PLACE_SELF if policy == "self" else N.PLACE_HRW
+        pol = {"self": N.PLACE_SELF, "hrw": N.PLACE_HRW, "hrw2": N.PLACE_HRW2}[policy]
         self_idx = 0
         if pol == N.PLACE_SELF:
             self_idx = self.node_index(self_address)
@@ -303,7 +312,7 @@ class Resolver:
     def __init__(self, provider, policy="hrw", self_address=None, max_batch=4096, max_wait_us=50):
         self.p = provider
         self.L = provider.L
-        pol = N.PLACE_SELF if policy == "self" else N.PLACE_HRW
+        pol = {"self": N.PLACE_SELF, "hrw": N.PLACE_HRW, "hrw2": N.PLACE_HRW2}[policy]
         self_idx = 0
         if pol == N.PLACE_SELF:
             self_idx = provider.node_index(self_address)

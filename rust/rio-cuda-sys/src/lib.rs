@@ -1,4 +1,4 @@
-//! Raw bindings for `include/rio_cuda.h` (ABI version 1).  One declaration per exported symbol.
+//! Raw bindings for `include/rio_cuda.h` (ABI version 2).  One declaration per exported symbol.
 #![allow(non_camel_case_types)]
 use libc::{c_char, c_void, size_t};
 
@@ -9,6 +9,9 @@ pub const RIO_ERR_UNKNOWN: rio_status = -2; // -> ObjectPlacementError::Unknown
 pub const RIO_NONE: u32 = 0xFFFF_FFFF;
 pub const RIO_PLACE_SELF: u32 = 0;
 pub const RIO_PLACE_HRW: u32 = 1;
+pub const RIO_PLACE_HRW2: u32 = 2;
+pub const RIO_SOLVER_HRW: u32 = 1;
+pub const RIO_SOLVER_HRW2: u32 = 2;
 pub const RIO_EV_JOIN: u32 = 1;
 pub const RIO_EV_LEAVE: u32 = 2;
 pub const RIO_COMM_ID_BYTES: usize = 128;
@@ -54,6 +57,8 @@ extern "C" {
     pub fn rio_cuda_node_intern(h: *mut rio_placement, address: *const c_char, out_idx: *mut u32) -> rio_status;
     pub fn rio_cuda_node_address(h: *mut rio_placement, idx: u32, buf: *mut c_char, cap: size_t, out_len: *mut size_t) -> rio_status;
     pub fn rio_cuda_node_count(h: *mut rio_placement, out_total: *mut u32, out_live: *mut u32) -> rio_status;
+    pub fn rio_cuda_set_solver(h: *mut rio_placement, solver: u32, trie_bits: u32) -> rio_status;
+    pub fn rio_cuda_get_solver(h: *mut rio_placement, solver: *mut u32, trie_bits: *mut u32) -> rio_status;
 
     pub fn rio_cuda_lookup_batch(h: *mut rio_placement, keys: *const u64, n: size_t, out_idx: *mut u32) -> rio_status;
     pub fn rio_cuda_upsert_batch(h: *mut rio_placement, keys: *const u64, idx: *const u32, n: size_t) -> rio_status;

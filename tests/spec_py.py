@@ -118,3 +118,80 @@ def assign_bounded(keys, seeds, weights, num=5, den=4, max_rounds=4):
 
 def synth_key(i, seed):
     return mix64((0x9E3779B97F4A7C15 * (i + 1) & M64) ^ seed)
+
+
+# ---- 3.8 HRW2: hierarchical weighted rendezvous with fan-out 2 -----------------------------------------------------
+# Written from the spec text as a literal recursion over sets of members (no sorting tricks, no prefix sums, no heap):
+# deliberately the slowest and most obvious of the three implementations.
+SALT_POS = 0x8CB92BA72F3D8DD7
+SALT_LVL = 0x3C79AC492BA7B653
+
+
+def hrw2_v(key, seed):
+    h = mix64(key ^ 0xD6E8FEB86659FD93)
+    a = h & M32
+    b = (h >> 32) | 1
+    ab = a * b & M32
+    p = ((seed & M32) * b + ab) & M32
+    m = (seed >> 32) | 1
+    s2 = mix64(seed ^ 0xA0761D6478BD642F) & M32
+    return (p * m + (s2 & 0x7FFFFFFF)) & 0x7FFFFFFF
+
+
+def hrw2_level_seed(level):
+    return mix64((0x9E3779B97F4A7C15 * (level + 1) & M64) ^ SALT_LVL)
+
+
+def hrw2_contest_left(key, contest_seed, wl, wr):
+    t = (wl << 31) // (wl + wr) if wl + wr else 0
+    return hrw2_v(key, contest_seed) < t
+
+
+def hrw2(key, seeds, weights, closed=(), bits=12):
+    members = [(mix64(s ^ SALT_POS), j) for j, (s, w) in enumerate(zip(seeds, weights)) if w and j not in closed]
+    if not members:
+        return NONE
+    for level in range(bits):
+        shift = 63 - level
+        left = [m for m in members if not (m[0] >> shift) & 1]
+        right = [m for m in members if (m[0] >> shift) & 1]
+        wl = sum(weights[j] for _, j in left)
+        wr = sum(weights[j] for _, j in right)
+        members = left if hrw2_contest_left(key, hrw2_level_seed(level), wl, wr) else right
+    members.sort()
+    while len(members) > 1:
+        (_, j), rest = members[0], members[1:]
+        if hrw2_contest_left(key, seeds[j], weights[j], sum(weights[i] for _, i in rest)):
+            return j
+        members = rest
+    return members[0][1]
+
+
+def assign_bounded_hrw2(keys, seeds, weights, num=5, den=4, max_rounds=4, bits=12):
+    n, M = len(keys), len(seeds)
+    W = sum(weights)
+    cap = [capacity(n, w, W, num, den) for w in weights]
+    idx = [hrw2(k, seeds, weights, (), bits) for k in keys]
+    closed = set()
+    passes = 1
+    for r in range(1, max_rounds):
+        c = [0] * M
+        for j in idx:
+            if j != NONE:
+                c[j] += 1
+        over = {j for j in range(M) if weights[j] and c[j] > cap[j]}
+        closed |= over
+        open_ = [j for j in range(M) if weights[j] and j not in closed]
+        if not over or not open_:
+            break
+        thr = {j: ((c[j] - cap[j]) << 32) // c[j] for j in over}
+        for i, k in enumerate(keys):
+            j = idx[i]
+            if j in over and spill_hash(k, r) < thr[j]:
+                idx[i] = hrw2(k, seeds, weights, closed, bits)
+        passes += 1
+    c = [0] * M
+    for j in idx:
+        if j != NONE:
+            c[j] += 1
+    return idx, c, passes

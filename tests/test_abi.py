@@ -41,7 +41,7 @@ def test_library_exports_every_declared_symbol(native):
 def test_binding_covers_every_declared_symbol(native):
     assert sorted(native.SIGNATURES) == _declared()
     native.lib()
-    assert native.lib().rio_cuda_abi_version() == 1
+    assert native.lib().rio_cuda_abi_version() == 2
 
 
 def test_host_key_helpers_match_oracle(native, oracle):

@@ -245,7 +245,7 @@ def test_edge_cases_empty_dead_and_raw_keys(gp, oracle):
 def test_golden_vectors_on_gpu(gp):
     import json
 
-    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "solver_v1.json")))
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "solver_hrw_v3.json")))
     p = provider(gp)
     p.set_nodes(g["hrw"]["addresses"], np.array(g["hrw"]["weights"], dtype=np.uint32))
     keys = np.array([int(k) for k in g["hrw"]["keys"]], dtype=np.uint64)

@@ -162,7 +162,7 @@ def test_affinity_oracle_against_numpy(oracle):
 
 def test_golden_vectors(oracle):
     """Committed vectors (generated by tests/golden/make_golden.py from spec_py) pin the spec across rounds."""
-    g = json.load(open(os.path.join(GOLD, "solver_v1.json")))
+    g = json.load(open(os.path.join(GOLD, "solver_hrw_v3.json")))
     L = oracle.lib()
     for k, v in g["mix64"]:
         assert L.orc_mix64(int(k)) == int(v)
