@@ -6,18 +6,21 @@
 
 Workload (config.workload): BASELINE.json configs[3] -- weighted rendezvous placement of 10 M objects x 1024 nodes
 (weights u32 in [1,16], seed 7; keys = splitmix stream), id-range sharded one shard per GPU, with the bounded-load
-capacity check after ONE all-gather of the per-node load counters (cap 1.25, <= 4 rounds).  Weak scaling: every rank
+capacity check after ONE exchange of the per-node load counters (cap 1.25, <= 4 rounds).  Weak scaling: every rank
 owns a 10 M-object shard, so N GPUs place N x 10 M objects per step.
 
+Policy (config.policy): HRW2, the hierarchical weighted rendezvous with fan-out 2 (~13 contests per
+object, HBM / shared-memory bound).  The flat rendezvous (1024 pair hashes per object, integer-pipe bound by construction)
+is timed beside it in `policies`.
+
 A step  = one bounded-load assignment pass over the rank's resident shard (keys already in HBM, results stay in HBM):
-          score grid + argmin kernel with fused per-node histogram -> counter all-gather -> capacity check.
+          walk kernel with fused per-node histogram -> counter exchange + capacity check (one small kernel) -> 8 bytes to
+          the host.
 value   = objects placed by all ranks per second over K steps (CUDA events on the engine's stream, max over ranks).
-e2e     = the same placements through the host-buffer C-ABI call rio_cuda_assign_batch (pinned host keys in, pinned host
-          node indices out, H2D + D2H inside the timed region).
-roofline= the assign kernel alone: algorithmic HBM bytes (12 B/object) / its launch time against the measured HBM peak;
-          the kernel is integer-ALU bound by construction (1024 pair hashes per 12 bytes), so `alu_roofline` reports
-          pair hashes/s against a register-only probe of the same instruction mix measured in the same run.
-cpu_baseline = this repo's CPU port of the same solver spec (oracle/rio_oracle.c), all host cores, bounded sample.
+e2e     = the SAME work through the host-buffer C-ABI call rio_cuda_assign_bounded_batch (pinned host keys in, pinned host
+          node indices out, histogram + exchange + capacity check included, H2D + D2H inside the timed region).
+roofline= the walk kernel alone: algorithmic HBM bytes (12 B/object) / its launch time against the measured HBM peak.
+cpu_baseline = this repo's CPU port of the same policy (oracle/rio_oracle.c), all host cores, bounded sample.
 --impl reference = the reference's own per-id CPU path (LocalObjectPlacement + Service::get_or_create_placement, restated
           in oracle/directory_model.cpp because rio-rs is Rust and no cargo exists here), all host threads.
 """
@@ -41,62 +44,82 @@ N_NODES = 1024
 N_SETS = 4  # distinct resident key sets rotated step to step: 4 x 120 MB of traffic > 126 MB of L2
 ALGO_BYTES_PER_OBJECT = 12  # 8 B key read + 4 B node index written
 HBM_FALLBACK_GBS = 6650.0
+TRIE_BITS = 12
+STORM_EVENTS = [("leave", 17), ("join", 1024), ("leave", 3), ("join", 1025), ("leave", 900), ("join", 1026), ("leave", 64), ("join", 1027)]
 
 
-def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the assign kernel from the committed ncu capture."""
-    p = os.path.join(ROOT, "profiles", "r01_ncu_assign_v3.json")
+def ncu_traffic(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel from the committed ncu capture."""
+    p = os.path.join(ROOT, "profiles", name)
     try:
         return float(json.load(open(p))["dram_bytes_per_launch"]), os.path.relpath(p, ROOT)
     except Exception:
         return None, None
 
 
-def measured_peaks():
+def measured(key, fallback):
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
             d = json.load(open(p))
-            if "hbm_gbs" in d:
-                return float(d["hbm_gbs"]), "measured"
+            if key in d:
+                return float(d[key]), "measured"
         except Exception:
             pass
-    return HBM_FALLBACK_GBS, "fallback"
+    return fallback, "fallback"
 
 
-def measured_tensor_peak():
-    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(p):
-        try:
-            d = json.load(open(p))
-            if "bf16_tflops" in d:
-                return float(d["bf16_tflops"]), "measured"
-        except Exception:
-            pass
-    return 1590.0, "fallback"
+def bind_to_gpu_numa(local_rank):
+    """Pin this rank's threads (and therefore its pinned allocations, first touch) to the CPUs of the NUMA node its GPU hangs
+    off: eight ranks pushing 80 MB each across the socket interconnect cost 15 % of the end-to-end rate in round 1."""
+    try:
+        import torch
+
+        bus = torch.cuda.get_device_properties(local_rank)
+        pci = "%04x:%02x:%02x.0" % (getattr(bus, "pci_domain_id", 0), bus.pci_bus_id, bus.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % pci).read())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus)}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)}
 
 
-def extra_configs(p, O, n, seeds_unused):
+def time_loop(p, fn, reps, slot=0):
+    p.sync()
+    p.event_record(slot)
+    for i in range(reps):
+        fn(i)
+    p.event_record(slot + 1)
+    p.sync()
+    return p.event_elapsed_ms(slot, slot + 1) / reps
+
+
+def extra_configs(p, O, n):
     """The other single-GPU configs of BASELINE.json, measured with the same event discipline (N = 1 only):
     C2 = 1 M x 64 weighted rendezvous; C3 = 10 M x 1024, 16-dim affinity cost + argmin on the tensor cores."""
     import rio_rs_b200 as R
 
     out = {}
     q = R.GpuObjectPlacement(device=p.device_info()["device"])
-    addrs, _, w = O.synth_nodes(64)
+    addrs, seeds, w = O.synth_nodes(64)
     q.set_nodes(addrs, w)
     s = q.new_set(1 << 20)
     s.synth_keys(0, 1 << 20, 1)
-    for _ in range(5):
-        s.assign()
-    q.sync()
-    q.event_record(0)
-    for _ in range(50):
-        s.assign()
-    q.event_record(1)
-    q.sync()
-    ms = q.event_elapsed_ms(0, 1) / 50
-    out["C2_rendezvous_1Mx64"] = {"ms": ms, "placements_per_s": (1 << 20) / (ms * 1e-3), "note": "resident keys, weights 1..16"}
+    for solver in ("hrw2", "hrw"):
+        q.set_solver(solver, TRIE_BITS)
+        for _ in range(5):
+            s.assign()
+        ms = time_loop(q, lambda i: s.assign(), 50)
+        ref = O.assign_hrw2(O.synth_keys(20000, 1), seeds, w, bits=TRIE_BITS) if solver == "hrw2" else O.assign_hrw(O.synth_keys(20000, 1), seeds, w)
+        out["C2_rendezvous_1Mx64_" + solver] = {"ms": ms, "placements_per_s": (1 << 20) / (ms * 1e-3), "parity_vs_oracle_20k": bool((s.read(0, 20000) == ref).all()),
+                                               "note": "resident keys, weights 1..16"}
+    q.set_solver("hrw")
     del s
     M, K = 1024, 16
     addrs, _, _ = O.synth_nodes(M)
@@ -108,24 +131,17 @@ def extra_configs(p, O, n, seeds_unused):
     s.load_feats(fo)
     for _ in range(3):
         s.assign(True)
-    q.sync()
-    q.event_record(0)
-    for _ in range(10):
-        s.assign(True)
-    q.event_record(1)
-    q.sync()
-    ms = q.event_elapsed_ms(0, 1) / 10
-    # parity spot-check of the tensor-core path against the fp64 oracle (checker only)
+    ms = time_loop(q, lambda i: s.assign(True), 10)
     got = s.read(0, 20000)
     idx, cost, gap = O.assign_affinity(fo[:20000], fn, np.ones(M, dtype=np.uint32), threads=8)
     ok = bool(((got == idx) | (gap <= 1e-5 * np.abs(cost) + 1e-12)).all())
-    peak, src = measured_tensor_peak()
-    issued = 6 * 2 * K * M * n / (ms * 1e-3) / 1e12  # six bf16 cross-term MMAs per (object, node) pair
+    peak, src = measured("bf16_tflops", 1590.0)
+    algo = 2 * K * M * n / (ms * 1e-3) / 1e12
     out["C3_affinity_10Mx1024xK16"] = {
         "ms": ms, "placements_per_s": n / (ms * 1e-3), "kernels": "k_affinity_umma (tcgen05/TMEM, bf16x3 split) + k_affinity_resolve",
         "parity_vs_fp64_oracle_20k": ok,
-        "roofline": {"bound": "tensor", "achieved": issued, "peak": peak, "unit": "TFLOP/s", "frac": issued / peak, "peak_source": src,
-                     "note": "bf16 FLOP/s actually issued (6 cross terms); algorithmic 2KM FLOP/s = achieved / 6"},
+        "roofline": {"bound": "tensor", "achieved": algo, "peak": peak, "unit": "TFLOP/s", "frac": algo / peak, "peak_source": src + " (burst figure: a 1-2 ms kernel timed alone)",
+                     "issued_bf16_tflops": 6 * algo, "note": "achieved = ALGORITHMIC 2KM FLOP per object; the kernel issues 6 bf16 cross-term MMAs per product (issued = 6 x achieved)"},
     }
     return out
 
@@ -145,7 +161,7 @@ class ClockSampler:
             return
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", self.idx, "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                ["nvidia-smi", "-i", self.idx, "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -163,7 +179,7 @@ class ClockSampler:
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+        time.sleep(0.15)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -204,22 +220,23 @@ def run_reference(args, rank, world):
 
     cores = os.cpu_count() or 1
     per_step = 400_000
+    steps = min(args.steps, 50)   # bounded: the whole arm ends within a few minutes whatever K the caller passes
     O.bench_resolve(20_000, N_NODES, cores)  # warm caches / allocator
-    for _ in range(max(args.warmup, 0)):
+    for _ in range(max(min(args.warmup, 5), 0)):
         O.bench_resolve(per_step // 4, N_NODES, cores)
     tot_s, tot_n = 0.0, 0
-    for k in range(args.steps):
+    for k in range(steps):
         s, placed = O.bench_resolve(per_step, N_NODES, cores, first=k * per_step)
         tot_s += s
         tot_n += placed
     v = tot_n / tot_s
-    sample = "%d steps x %d fresh ids ('Obj', decimal i) resolved per-id against a %d-member cluster" % (args.steps, per_step, N_NODES)
+    sample = "%d steps x %d fresh ids ('Obj', decimal i) resolved per-id against a %d-member cluster" % (steps, per_step, N_NODES)
     line = {
         "impl": "reference", "metric": "placements/sec", "value": v, "unit": "placements/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / max(steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
         "config": {"workload": "10M objects x 1024 nodes placement (BASELINE.json configs[3]); reference policy: first server to see the id claims it",
-                   "objects_per_step": per_step, "nodes": N_NODES},
+                   "objects_per_step": per_step, "nodes": N_NODES, "steps_run": steps},
         "cpu_baseline": {"value": v, "unit": "placements/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "placements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -256,14 +273,15 @@ def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=5000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--objects", type=int, default=N_OBJECTS, help="objects per rank (default: the BASELINE size)")
     ap.add_argument("--nodes", type=int, default=N_NODES)
+    ap.add_argument("--policy", default="hrw2", choices=["hrw2", "hrw"], help="headline solver policy (the other one is timed in `policies`)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-extra", action="store_true", help="skip the C2/C3 side measurements (N = 1 only)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C2/C3/C4-strong/C5 side measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -280,6 +298,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -295,16 +314,21 @@ def main():
         dist.barrier()
     import rio_rs_b200 as R
     from rio_rs_b200 import parallel
-    from oracle import pyoracle as O  # synthetic-input helpers + the cpu_baseline leg only
+    from oracle import pyoracle as O  # synthetic-input helpers, the in-bench parity checks and the cpu_baseline leg only
 
     n, M = args.objects, args.nodes
     p = R.GpuObjectPlacement(device=local_rank)
     info = p.device_info()
     addrs, seeds, w = O.synth_nodes(M)
     p.set_nodes(addrs, w)
+    p.set_solver(args.policy, TRIE_BITS)
     if dist:
         parallel.init_comm(p, dist)
     n_global = n * world
+    cores = os.cpu_count() or 1
+
+    def oracle_assign(keys, solver, weights=w, threads=8):
+        return O.assign_hrw2(keys, seeds, weights, bits=TRIE_BITS, threads=threads) if solver == "hrw2" else O.assign_hrw(keys, seeds, weights, threads=threads)
 
     def barrier_sync():
         p.sync()
@@ -318,6 +342,13 @@ def main():
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    def all_ranks_ok(ok):
+        if not dist:
+            return bool(ok)
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
 
     # resident shards: id range [rank*n, (rank+1)*n) of N_SETS independent key streams
     sets = []
@@ -339,7 +370,7 @@ def main():
         passes = step(i)
     barrier_sync()
     if clocks:
-        time.sleep(0.3)   # make sure the sampler is producing before the timed region starts
+        time.sleep(0.25)   # make sure the sampler is producing before the timed region starts
         clocks.mark()
     barrier_sync()
     l0 = p.launch_count()
@@ -353,88 +384,178 @@ def main():
     ms_per_step = ms_total / args.steps
     value = n_global / (ms_per_step * 1e-3)
 
-    # the dominant kernel alone (score grid + argmin + fused histogram), same resident inputs, events on its stream
-    for i in range(3):
+    # the dominant kernel alone (walk + fused histogram), same resident inputs, events on its stream
+    kreps = max(20, min(args.steps, 2000))
+    for i in range(5):
         sets[i % N_SETS].assign()
-    p.sync()
-    p.event_record(2)
-    for i in range(args.steps):
-        sets[i % N_SETS].assign()
-    p.event_record(3)
-    p.sync()
+    kern_ms = time_loop(p, lambda i: sets[i % N_SETS].assign(), kreps, 2)
     if clocks and len(clocks.lines) < 3 * world:   # short runs: keep the same kernel running until a few samples exist
-        t_end = time.perf_counter() + 0.6
+        t_end = time.perf_counter() + 0.5
         while time.perf_counter() < t_end:
-            for i in range(10):
+            for i in range(50):
                 sets[i % N_SETS].assign()
             p.sync()
     clk = clocks.stop() if clocks else None   # covers the timed steps, the kernel-only loop (and the burst above, if any)
-    kern_ms = p.event_elapsed_ms(2, 3) / args.steps
-    peak, peak_src = measured_peaks()
-    traffic, traffic_src = ncu_traffic() if (n == N_OBJECTS and M == N_NODES) else (None, None)
+    peak, peak_src = measured("hbm_gbs", HBM_FALLBACK_GBS)
+    kernel_name = "k_assign_trie" if args.policy == "hrw2" else "k_assign_hrw_v2"
+    traffic, traffic_src = ncu_traffic("r02_ncu_trie.json" if args.policy == "hrw2" else "r01_ncu_assign_v3.json") if (n == N_OBJECTS and M == N_NODES) else (None, None)
     achieved_gbs = ALGO_BYTES_PER_OBJECT * n / (kern_ms * 1e-3) / 1e9
-    pair_rate = n * M / (kern_ms * 1e-3)
-    mix_peak = max(p.bench_mix_rate(4000) for _ in range(3))
 
-    # e2e: host buffers through the C ABI (H2D + grid + D2H, chunk-pipelined)
+    # the headline result against the oracle: the FIRST shard-local 200k objects of set 0 on every rank
+    chk = sets[0].read(0, min(n, 200_000))
+    parity_ok = all_ranks_ok((chk == oracle_assign(O.synth_keys(len(chk), 1, first=rank * n), args.policy)).all())
+    assert parity_ok, "GPU result differs from the oracle"
+
+    # both policies on the same resident inputs (kernel alone + full bounded step)
+    policies = {}
+    for solver in ("hrw2", "hrw"):
+        p.set_solver(solver, TRIE_BITS)
+        reps = kreps if solver == "hrw2" else 10
+        for i in range(3):
+            sets[i % N_SETS].assign()
+        k_ms = time_loop(p, lambda i: sets[i % N_SETS].assign(), reps, 2)
+        barrier_sync()
+        s_ms = max_over_ranks(time_loop(p, lambda i: sets[i % N_SETS].assign_bounded(n_global, 5, 4, 4), reps, 4))
+        ok = bool((sets[0].read(0, 50_000) == oracle_assign(O.synth_keys(50_000, 1, first=rank * n), solver)).all())
+        policies[solver] = {"kernel_ms": k_ms, "step_ms": s_ms, "placements_per_s_step": n_global / (s_ms * 1e-3), "hbm_frac_kernel": ALGO_BYTES_PER_OBJECT * n / (k_ms * 1e-3) / 1e9 / peak,
+                            "contests_or_pair_hashes_per_object": (TRIE_BITS + 1) if solver == "hrw2" else M, "parity_vs_oracle_50k": ok}
+        if solver == "hrw":
+            mix_peak = max(p.bench_mix_rate(4000) for _ in range(3))
+            policies[solver]["alu_roofline"] = {"bound": "int-alu", "achieved": n * M / (k_ms * 1e-3), "peak": mix_peak, "unit": "pair-hashes/s", "frac": n * M / (k_ms * 1e-3) / mix_peak,
+                                                "peak_source": "rio_cuda_bench_mix_rate: register-only replay of the same IMAD/IMAD/VIMNMX3 mix, measured in this run"}
+    p.set_solver(args.policy, TRIE_BITS)
+    sets[0].assign_bounded(n_global, 5, 4, 4)   # set 0 holds the headline policy's result again (the e2e leg compares against it)
+
+    # multi-rank bounded rounds where they actually fire: cap 101/100 on a 400k-object shard per rank (passes > 1), every
+    # rank's result against the oracle run on the GLOBAL key set -- decisions taken on global counters must agree bit for bit
+    multi_rank = None
+    if world > 1:
+        m_per = 400_000
+        t = p.new_set(m_per)
+        t.synth_keys(rank * m_per, m_per, 9)
+        got_passes = t.assign_bounded(m_per * world, 101, 100, 4)
+        gkeys = O.synth_keys(m_per * world, 9)
+        if args.policy == "hrw2":
+            widx, wcnt, wpass = O.assign_bounded_hrw2(gkeys, seeds, w, 101, 100, 4, bits=TRIE_BITS, threads=max(1, cores // world))
+        else:
+            widx, wcnt, wpass = O.assign_bounded(gkeys, seeds, w, 101, 100, 4, threads=max(1, cores // world))
+        ok = bool((t.read() == widx[rank * m_per:(rank + 1) * m_per]).all() and got_passes == wpass and (t.counters() == wcnt).all())
+        multi_rank = {"objects_per_rank": m_per, "cap": "101/100", "passes": got_passes, "oracle_passes": int(wpass), "all_ranks_equal_oracle": all_ranks_ok(ok)}
+        del t
+
+    # e2e: host buffers through the C ABI, same work as `value` (H2D + walk + histogram + exchange + check + D2H, chunk-pipelined)
     e2e = None
     if not args.no_e2e:
         hk, hk_ptr = pinned_array(p, n * 8, np.uint64)
         ho, ho_ptr = pinned_array(p, n * 4, np.uint32)
         hk[:] = O.synth_keys(n, 1, first=rank * n)
-        for _ in range(2):
-            p.assign_batch(hk, out=ho)
+        ereps = max(5, min(args.steps, 50))
+        for _ in range(3):
+            p.assign_bounded_batch(hk, n_global, 5, 4, 4, out=ho)
         barrier_sync()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            p.assign_batch(hk, out=ho)
+        for _ in range(ereps):
+            p.assign_bounded_batch(hk, n_global, 5, 4, 4, out=ho)
         p.sync()
         dt = max_over_ranks(time.perf_counter() - t0)
-        e2e_ms = 1e3 * dt / args.steps
+        e2e_ms = 1e3 * dt / ereps
         e2e = {"value": n_global / (e2e_ms * 1e-3), "unit": "placements/s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 4 * n,
-               "ms_per_step": e2e_ms, "api": "rio_cuda_assign_batch (pinned host keys -> pinned host node indices)"}
+               "ms_per_step": e2e_ms, "steps": ereps, "pcie_floor_ms_80MB_at_55GBps": 80e6 / 55e9 * 1e3 * (n / N_OBJECTS),
+               "api": "rio_cuda_assign_bounded_batch (pinned host keys -> pinned host node indices; fused histogram, counter exchange and capacity check included)"}
         # the result that came back over PCIe is the resident result
-        assert (ho[:100000] == sets[0].read(0, 100000)).all()
-
-    # parity spot-check inside the bench (the checker, never the thing measured)
-    chk = sets[0].read(0, 20000)
-    assert (chk == O.assign_hrw(O.synth_keys(20000, 1, first=rank * n), seeds, w, threads=4)).all(), "GPU result differs from the oracle"
+        assert (ho[:200_000] == sets[0].read(0, 200_000)).all()
+        if numa:
+            e2e["cpu_binding"] = numa
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        probe = O.synth_keys(20_000, 1)
-        t0 = time.perf_counter()
-        O.assign_hrw(probe, seeds, w, threads=cores)
-        rate = len(probe) / (time.perf_counter() - t0)
-        m = int(min(n, max(50_000, rate * 12)))  # ~12 s of CPU work
-        ks = O.synth_keys(m, 1)
-        t0 = time.perf_counter()
-        O.assign_hrw(ks, seeds, w, threads=cores)
+        ks = O.synth_keys(min(n, 10_000_000), 1)
+        oracle_assign(ks[:200_000], args.policy, threads=cores)
+        t0, done = time.perf_counter(), 0
+        while time.perf_counter() - t0 < 10.0:   # ~10 s of CPU work on all cores
+            oracle_assign(ks, args.policy, threads=cores)
+            done += len(ks)
         dt = time.perf_counter() - t0
-        cpu = {"value": m / dt, "unit": "placements/s", "cores": cores, "kind": "port",
-               "sample": "first %d of the 10M objects x %d nodes, oracle/rio_oracle.c orc_assign_hrw, %d threads, %.1f s" % (m, M, cores, dt)}
+        cpu = {"value": done / dt, "unit": "placements/s", "cores": cores, "kind": "port",
+               "sample": "%d passes over the first %d of the 10M objects x %d nodes, oracle/rio_oracle.c (%s), %d threads, %.1f s" % (
+                   done // len(ks), len(ks), M, "orc_assign_hrw2" if args.policy == "hrw2" else "orc_assign_hrw", cores, dt)}
+        if args.policy == "hrw2":   # the flat solver on the same cores, for context
+            kf = ks[:400_000]
+            t0 = time.perf_counter()
+            O.assign_hrw(kf, seeds, w, threads=cores)
+            cpu["flat_policy_value"] = len(kf) / (time.perf_counter() - t0)
 
     extra = None
-    if rank == 0 and world == 1 and n == N_OBJECTS and not args.no_extra:
+    if not args.no_extra and n == N_OBJECTS:
+        extra = {}
         try:
-            extra = extra_configs(p, O, n, seeds)
+            # C4 as BASELINE.json words it: 10 M objects TOTAL, id-range sharded over the ranks (strong scaling)
+            lo, hi = parallel.shard_range(N_OBJECTS, rank, world)
+            t = p.new_set(hi - lo)
+            t.synth_keys(lo, hi - lo, 1)
+            for _ in range(10):
+                t.assign_bounded(N_OBJECTS, 5, 4, 4)
+            barrier_sync()
+            sreps = max(20, min(args.steps, 1000))
+            ms = max_over_ranks(time_loop(p, lambda i: t.assign_bounded(N_OBJECTS, 5, 4, 4), sreps, 6))
+            ok = all_ranks_ok((t.read(0, min(hi - lo, 100_000)) == oracle_assign(O.synth_keys(min(hi - lo, 100_000), 1, first=lo), args.policy)).all())
+            extra["C4_strong_10M_total"] = {"ms_per_step": ms, "placements_per_s": N_OBJECTS / (ms * 1e-3), "objects_per_rank": hi - lo, "steps": sreps, "parity_vs_oracle": ok,
+                                            "note": "L2-resident at this size (one 10M/N shard re-walked); strong-scaling efficiency = this / (N x the N=1 figure)"}
+            del t
+            # C5: 100 M objects total, the fixed list of 8 join/leave events, one exchange of the counters per event
+            lo, hi = parallel.shard_range(100_000_000, rank, world)
+            q = R.GpuObjectPlacement(device=local_rank)
+            a5, s5, w5 = O.synth_nodes(M + 4)
+            q.set_nodes(a5[:M], w5[:M])
+            q.set_solver(args.policy, TRIE_BITS)
+            if dist:
+                parallel.init_comm(q, dist)
+            t = q.new_set(hi - lo)
+            t.synth_keys(lo, hi - lo, 1)
+            t.assign()
+            q.sync()
+            wl = w5.copy()
+            wl[M:] = 0
+            if dist:
+                dist.barrier()
+            t0 = time.perf_counter()
+            moved = []
+            for ev, j in STORM_EVENTS:
+                if ev == "leave":
+                    q.node_set_active(j, False)
+                    wl[j] = 0
+                else:
+                    q.node_upsert(a5[j], int(w5[j]))
+                    wl[j] = w5[j]
+                moved.append(t.rebalance(ev, j))
+                t.counters()   # the one exchange of the event
+            q.sync()
+            wall = max_over_ranks(time.perf_counter() - t0)
+            m5 = min(hi - lo, 100_000)
+            ok = all_ranks_ok((t.read(0, m5) == (O.assign_hrw2(O.synth_keys(m5, 1, first=lo), s5, wl, bits=TRIE_BITS, threads=8) if args.policy == "hrw2"
+                                                 else O.assign_hrw(O.synth_keys(m5, 1, first=lo), s5, wl, threads=8))).all())
+            extra["C5_storm_100M_8_events"] = {"wall_ms": wall * 1e3, "objects_total": 100_000_000, "objects_per_rank": hi - lo, "moved_on_rank0": moved,
+                                               "state_equals_fresh_assignment_sample": ok, "events": ["%s(%d)" % e for e in STORM_EVENTS]}
+            del t, q
+            if rank == 0 and world == 1:
+                extra.update(extra_configs(p, O, n))
         except Exception as e:  # the headline line must still be printed
-            extra = {"error": repr(e)}
+            extra["error"] = repr(e)
 
     if rank == 0:
         line = {
             "metric": "placements/sec", "value": value, "unit": "placements/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": "10M objects x 1024 nodes weighted-rendezvous placement, id-range shard per GPU, bounded-load check after one all-gather of load counters (BASELINE.json configs[3])",
+            "config": {"workload": "10M objects x 1024 nodes weighted-rendezvous placement, id-range shard per GPU, bounded-load check after one exchange of load counters (BASELINE.json configs[3])",
+                       "policy": ("hrw2: hierarchical weighted rendezvous, fan-out 2, trie_bits %d (DESIGN.md 3.8)" % TRIE_BITS) if args.policy == "hrw2" else "hrw: flat weighted rendezvous (DESIGN.md 3.4)",
                        "objects_per_gpu": n, "global_objects": n_global, "nodes": M, "weights": "u32 in [1,16], seed 7", "capacity": "1.25", "max_rounds": 4,
                        "passes_run": passes, "l2": "inputs larger than L2: %d resident key sets rotated step to step" % N_SETS, "parallelism": "id-range shard x%d" % world,
-                       "device": info["name"], "sms": info["sm_count"]},
+                       "parity_vs_oracle_200k_per_rank": parity_ok, "multi_rank_parity": multi_rank, "device": info["name"], "sms": info["sm_count"]},
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peak, "unit": "GB/s", "frac": achieved_gbs / peak, "traffic": traffic, "traffic_source": traffic_src,
-                         "kernel": "k_assign_hrw_v2", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_OBJECT * n, "peak_source": peak_src,
-                         "note": "integer-ALU bound by construction (1024 pair hashes per 12 B); see alu_roofline"},
-            "alu_roofline": {"bound": "int-alu", "achieved": pair_rate, "peak": mix_peak, "unit": "pair-hashes/s", "frac": pair_rate / mix_peak,
-                             "peak_source": "rio_cuda_bench_mix_rate: register-only replay of the same IMAD/IMAD/VIMNMX3 mix, measured in this run"},
+                         "kernel": kernel_name, "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_OBJECT * n, "peak_source": peak_src,
+                         "note": "12 B/object (8 B key in, 4 B node index out); the walk is bound by shared-memory gather wavefronts and the ALU pipe before HBM (profiles/r02_ncu_trie.json)"
+                         if args.policy == "hrw2" else "integer-ALU bound by construction (1024 pair hashes per 12 B); see policies.hrw.alu_roofline"},
+            "policies": policies,
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": int(launches),

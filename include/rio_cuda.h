@@ -130,6 +130,11 @@ rio_status  rio_cuda_directory_len(rio_placement *h, uint64_t *out_placed, uint6
  * (cost = -dot, argmin) and requires node features of the same K. */
 rio_status  rio_cuda_assign_batch(rio_placement *h, const uint64_t *keys, const float *obj_feats, size_t n,
                                   uint32_t *out_idx);
+/* assign_batch followed by the bounded-load rounds of rio_cuda_set_assign_bounded for host buffers: the
+ * per-node histogram is fused into the score kernels of the chunk pipeline, the counter exchange + capacity check runs on
+ * the device behind the last chunk.  n_total = global object count (0 = n * world).  Hash path only. */
+rio_status  rio_cuda_assign_bounded_batch(rio_placement *h, const uint64_t *keys, size_t n, uint64_t n_total, uint32_t cap_num,
+                                          uint32_t cap_den, uint32_t max_rounds, uint32_t *out_idx, uint32_t *out_passes);
 /* Service::get_or_create_placement for a batch (service.rs:193-254): existing & live => keep; recorded on an
  * inactive node => clean_server(that node) then re-place; none => place.  policy RIO_PLACE_SELF re-places on
  * self_idx (the reference's rule, service.rs:244-252); RIO_PLACE_HRW / RIO_PLACE_HRW2 re-place by the solver. */
@@ -138,6 +143,19 @@ rio_status  rio_cuda_assign_batch(rio_placement *h, const uint64_t *keys, const 
 #define RIO_PLACE_HRW2 2u   /* re-place by the hierarchical solver (RIO_SOLVER_HRW2 semantics, the handle's trie_bits) */
 rio_status  rio_cuda_place_batch(rio_placement *h, const uint64_t *keys, size_t n, uint32_t policy,
                                  uint32_t self_idx, uint32_t *out_idx);
+/* Service::check_address_mismatch for a batch (service.rs:261-298), the second half of the per-request policy: for the
+ * address index the first half returned, RIO_ADDR_LOCAL = it is this server (Ok(())); RIO_ADDR_REDIRECT = the node is active
+ * elsewhere (Err(Redirect(address))); RIO_ADDR_DEALLOCATE = the node is not active: clean_server(address) HAS BEEN APPLIED
+ * to the directory (one table scan for all such nodes of the batch) and the caller answers DeallocateServiceObject;
+ * RIO_ADDR_MALFORMED = the recorded address has no ':' (Err(Unknown("Malformed address: Missing PORT ..."))).  Like the
+ * reference, only the first two ':'-separated pieces of the address are the (ip, port) asked of is_active.
+ * out_cleaned (may be NULL) receives the number of directory entries the clean_server calls removed. */
+#define RIO_ADDR_LOCAL      0u
+#define RIO_ADDR_REDIRECT   1u
+#define RIO_ADDR_DEALLOCATE 2u
+#define RIO_ADDR_MALFORMED  3u
+rio_status  rio_cuda_check_address_batch(rio_placement *h, const uint32_t *addr_idx, size_t n, uint32_t self_idx,
+                                         uint8_t *out_verdict, uint64_t *out_cleaned);
 /* Eager re-placement of the whole directory after a membership change (replaces the lazy per-object path
  * service.rs:224-238 / 286-297): RIO_EV_JOIN(idx) moves onto idx exactly the objects that now prefer it;
  * RIO_EV_LEAVE(idx) re-places exactly the objects recorded on idx.  Under RIO_SOLVER_HRW2 every placed key is walked
@@ -153,8 +171,6 @@ rio_status  rio_cuda_load_counters(rio_placement *h, uint32_t *out, uint32_t cap
 rio_status  rio_cuda_set_create(rio_placement *h, uint64_t capacity, rio_objset **out);
 void        rio_cuda_set_destroy(rio_objset *s);
 rio_status  rio_cuda_set_load_keys(rio_objset *s, const uint64_t *keys, uint64_t n);      /* host -> HBM */
-/* key[i] = mix64(GOLDEN*(first+i+1) ^ seed): the synthetic stream of SURVEY 8d, generated in HBM */
-rio_status  rio_cuda_set_synth_keys(rio_objset *s, uint64_t first, uint64_t n, uint64_t seed);
 rio_status  rio_cuda_set_load_feats(rio_objset *s, const float *feats, uint32_t K);       /* n x K fp32 */
 /* (Re)assign every object of the set over the live nodes; counters of the result are kept on device. */
 rio_status  rio_cuda_set_assign(rio_objset *s, uint32_t use_affinity);
@@ -199,18 +215,6 @@ rio_status  rio_cuda_lookup_batch_dev(rio_placement *h, const uint64_t *d_keys, 
 rio_status  rio_cuda_upsert_batch_dev(rio_placement *h, const uint64_t *d_keys, const uint32_t *d_idx, size_t n);
 /* pre-size the directory for n more distinct keys (the _dev upsert cannot grow it mid-stream) */
 rio_status  rio_cuda_directory_reserve(rio_placement *h, uint64_t n_more);
-/* write `bytes` of zeros-then-ones through a scratch buffer larger than L2 (bench hygiene between steps) */
-rio_status  rio_cuda_flush_l2(rio_placement *h);
-
-/* ---- timing on the handle's stream (CUDA events; torch.cuda.Event cannot see this stream) --------------- */
-#define RIO_MAX_EVENTS 64
-rio_status  rio_cuda_event_record(rio_placement *h, uint32_t slot);
-rio_status  rio_cuda_event_elapsed_ms(rio_placement *h, uint32_t slot_start, uint32_t slot_end, float *out_ms);
-/* Integer-ALU roofline probe: a register-only replay of the rendezvous inner loop (same instruction mix, no memory
- * traffic); reports (object,node) pair hashes per second.  Event slots RIO_MAX_EVENTS-2/-1 are used internally. */
-rio_status  rio_cuda_bench_mix_rate(rio_placement *h, uint32_t iters, double *out_pairs_per_s);
-/* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
-rio_status  rio_cuda_launch_count(rio_placement *h, uint64_t *out);
 
 /* ---- string-level provider calls: exactly what `impl ObjectPlacement for GpuObjectPlacement` forwards ---- */
 /* update(ObjectPlacementItem): address==NULL is server_address: None (mod.rs:46-49, local.rs:34-38) */

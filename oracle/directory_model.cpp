@@ -128,9 +128,28 @@ std::string get_or_create_placement(Model &m, const std::string &self_address, c
     return self_address;                                                    // :252
 }
 
+/* Service::check_address_mismatch, service.rs:261-298.  Returns 0 = Ok(()), 1 = Err(Redirect(server_address)),
+ * 2 = clean_server(server_address) applied + Err(DeallocateServiceObject), 3 = Err(Unknown("Malformed address: Missing PORT ..")) */
+int check_address_mismatch(Model &m, const std::string &self_address, const std::string &server_address) {
+    if (server_address == self_address) return 0;                           // :262-264
+    // `split(':')` (not splitn): ip = first piece (always present), port = SECOND piece, further pieces ignored  :266-278
+    size_t c = server_address.find(':');
+    if (c == std::string::npos) return 3;                                   // "Missing PORT"
+    std::string ip = server_address.substr(0, c);
+    size_t c2 = server_address.find(':', c + 1);
+    std::string port = server_address.substr(c + 1, c2 == std::string::npos ? std::string::npos : c2 - c - 1);
+    if (m.mem.is_active(ip, port)) return 1;                                // :280-288
+    m.dir.clean_server(server_address.c_str());                             // :291-296
+    return 2;                                                               // :297
+}
+
 }  // namespace
 
 extern "C" {
+
+int dm_check_address_mismatch(void *h, const char *self_address, const char *server_address) {
+    return check_address_mismatch(*(Model *)h, self_address, server_address);
+}
 
 void *dm_new() { return new Model(); }
 void dm_free(void *h) { delete (Model *)h; }

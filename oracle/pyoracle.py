@@ -217,6 +217,8 @@ def dm():
         D.dm_member_is_active.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
         D.dm_get_or_create_placement.restype = C.c_int64
         D.dm_get_or_create_placement.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]
+        D.dm_check_address_mismatch.restype = C.c_int
+        D.dm_check_address_mismatch.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
         D.dm_bench_resolve.restype = C.c_double
         D.dm_bench_resolve.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]
         D.dm_bench_lookup.restype = C.c_double
@@ -274,6 +276,17 @@ class DirectoryModel:
     def get_or_create_placement(self, self_address, type_, id_):
         n = self._d.dm_get_or_create_placement(self._h, self_address.encode(), type_.encode(), id_.encode(), self._buf, 256)
         return self._buf.raw[:n].decode()
+
+
+ADDR_LOCAL, ADDR_REDIRECT, ADDR_DEALLOCATE, ADDR_MALFORMED = 0, 1, 2, 3
+
+
+def _dm_check_address_mismatch(self, self_address, server_address):
+    """service.rs:261-298 -> ADDR_LOCAL (Ok) | ADDR_REDIRECT | ADDR_DEALLOCATE (clean_server applied) | ADDR_MALFORMED"""
+    return int(self._d.dm_check_address_mismatch(self._h, self_address.encode(), server_address.encode()))
+
+
+DirectoryModel.check_address_mismatch = _dm_check_address_mismatch
 
 
 def bench_resolve(n, M, threads, first=0):

@@ -57,13 +57,14 @@ SIGNATURES = {
     "rio_cuda_clean_node": (C.c_int32, [H, C.c_uint32, u64p]),
     "rio_cuda_directory_len": (C.c_int32, [H, u64p, u64p]),
     "rio_cuda_assign_batch": (C.c_int32, [H, vp, vp, sz, vp]),
+    "rio_cuda_assign_bounded_batch": (C.c_int32, [H, vp, sz, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, vp, u32p]),
+    "rio_cuda_check_address_batch": (C.c_int32, [H, vp, sz, C.c_uint32, vp, u64p]),
     "rio_cuda_place_batch": (C.c_int32, [H, vp, sz, C.c_uint32, C.c_uint32, vp]),
     "rio_cuda_rebalance": (C.c_int32, [H, C.c_uint32, C.c_uint32, u64p]),
     "rio_cuda_load_counters": (C.c_int32, [H, vp, C.c_uint32]),
     "rio_cuda_set_create": (C.c_int32, [H, C.c_uint64, C.POINTER(H)]),
     "rio_cuda_set_destroy": (None, [H]),
     "rio_cuda_set_load_keys": (C.c_int32, [H, vp, C.c_uint64]),
-    "rio_cuda_set_synth_keys": (C.c_int32, [H, C.c_uint64, C.c_uint64, C.c_uint64]),
     "rio_cuda_set_load_feats": (C.c_int32, [H, vp, C.c_uint32]),
     "rio_cuda_set_assign": (C.c_int32, [H, C.c_uint32]),
     "rio_cuda_set_assign_bounded": (C.c_int32, [H, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, u32p]),
@@ -88,11 +89,6 @@ SIGNATURES = {
     "rio_cuda_lookup_batch_dev": (C.c_int32, [H, vp, sz, vp]),
     "rio_cuda_upsert_batch_dev": (C.c_int32, [H, vp, vp, sz]),
     "rio_cuda_directory_reserve": (C.c_int32, [H, C.c_uint64]),
-    "rio_cuda_flush_l2": (C.c_int32, [H]),
-    "rio_cuda_event_record": (C.c_int32, [H, C.c_uint32]),
-    "rio_cuda_event_elapsed_ms": (C.c_int32, [H, C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]),
-    "rio_cuda_bench_mix_rate": (C.c_int32, [H, C.c_uint32, C.POINTER(C.c_double)]),
-    "rio_cuda_launch_count": (C.c_int32, [H, u64p]),
     "rio_cuda_resolver_create": (C.c_int32, [H, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(H)]),
     "rio_cuda_resolver_destroy": (None, [H]),
     "rio_cuda_resolver_resolve": (C.c_int32, [H, C.c_uint64, u32p]),
@@ -104,6 +100,21 @@ SIGNATURES = {
     "rio_cuda_clean_server_str": (C.c_int32, [H, C.c_char_p, sz]),
     "rio_cuda_remove_str": (C.c_int32, [H, C.c_char_p, sz, C.c_char_p, sz]),
 }
+
+# include/rio_cuda_dev.h: measurement and test hooks, not part of the provider ABI
+DEV_SIGNATURES = {
+    "rio_cuda_set_synth_keys": (C.c_int32, [H, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "rio_cuda_flush_l2": (C.c_int32, [H]),
+    "rio_cuda_event_record": (C.c_int32, [H, C.c_uint32]),
+    "rio_cuda_event_elapsed_ms": (C.c_int32, [H, C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]),
+    "rio_cuda_bench_mix_rate": (C.c_int32, [H, C.c_uint32, C.POINTER(C.c_double)]),
+    "rio_cuda_launch_count": (C.c_int32, [H, u64p]),
+    "rio_dev_set_node_seed": (C.c_int32, [H, C.c_uint32, C.c_uint64]),
+    "rio_dev_set_table_options": (C.c_int32, [H, C.c_uint32]),
+    "rio_dev_umma_timing": (C.c_int32, [H, vp]),
+}
+ADDR_LOCAL, ADDR_REDIRECT, ADDR_DEALLOCATE, ADDR_MALFORMED = 0, 1, 2, 3
+DEV_SPLIT_CLASSES = 1
 
 
 def lib():
@@ -117,7 +128,7 @@ def lib():
                 "(nvcc, sm_100a).  There is no CPU fallback."
             )
         L = C.CDLL(path)
-        for name, (res, args) in SIGNATURES.items():
+        for name, (res, args) in list(SIGNATURES.items()) + list(DEV_SIGNATURES.items()):
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "librio_cuda.so")
 SOURCES = ["k_assign.cu", "k_trie.cu", "k_affinity_umma.cu", "k_directory.cu", "engine.cu", "resolver.cu"]
-HEADERS = ["kernels.cuh", "spec.cuh", os.path.join("..", "..", "include", "rio_cuda.h")]
+HEADERS = ["kernels.cuh", "spec.cuh", os.path.join("..", "..", "include", "rio_cuda.h"), os.path.join("..", "..", "include", "rio_cuda_dev.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -31,10 +31,11 @@ def is_fresh():
 
 
 def build(force=False, verbose=False):
-    """Compile every CUDA source of the product into rio_rs_b200/librio_cuda.so."""
+    """Compile every CUDA source of the product into rio_rs_b200/librio_cuda.so.  RIO_BUILD_TUNING=1 also compiles the A/B
+    tuning points of the flat rendezvous kernel (tools/tune_assign.py); the shipped library carries the default only."""
     if not force and is_fresh():
         return SO
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-DRIO_ASSIGN_TUNING"] if os.environ.get("RIO_BUILD_TUNING") else []) + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
     env = dict(os.environ)
     env.pop("CC", None)   # the image exports CC=/opt/gcc/bin/gcc; nvcc should use the system g++
     env.pop("CXX", None)

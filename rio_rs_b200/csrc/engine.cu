@@ -5,6 +5,7 @@
 // around it (rio-rs/src/service.rs:193-254).  There is NO CPU fallback anywhere in this file: without a CUDA
 // device rio_cuda_create fails with RIO_ERR_UPSTREAM.
 #include "../../include/rio_cuda.h"
+#include "../../include/rio_cuda_dev.h"
 #include "kernels.cuh"
 #include "spec.cuh"
 
@@ -115,7 +116,7 @@ struct TabBufs {
 };
 
 // device scalars (one small allocation): [0]=nsel [1]=moved/removed [2]=new keys (cumulative) [3]=placed ; u32 error at [8]
-enum { S_NSEL = 0, S_MOVED = 1, S_NEWKEYS = 2, S_PLACED = 3, S_COUNT = 8 };
+enum { S_NSEL = 0, S_MOVED = 1, S_NEWKEYS = 2, S_PLACED = 3, S_FLAGS = 4 /* host-only: {any over, open nodes} written by k_exchange_check */, S_COUNT = 8 };
 
 }  // namespace
 
@@ -130,6 +131,7 @@ struct rio_placement {
     std::vector<NodeInfo> nodes;
     std::unordered_map<std::string, uint32_t> node_index;
     uint32_t K = 0;
+    uint32_t dev_table_flags = 0;       // rio_dev_set_table_options
     uint32_t solver = RIO_SOLVER_HRW;   // policy of assign_batch / set_assign / rebalance (rio_cuda_set_solver)
     uint32_t trie_bits = 12;            // HRW2: depth of the binary trie over node positions
     bool tab_dirty = true;
@@ -144,6 +146,10 @@ struct rio_placement {
     uint32_t dir_seq = 0;           // upsert sequence numbers handed out so far (ordering of duplicate keys, k_dir_upsert)
 
     DevBuf s_keys, s_idx, s_idx2, s_sel, s_slots, s_keys2, s_feats, s_packed, s_offsets, s_cost, s_misc, s_flush, s_gather;
+    // bounded-load state kept on the device between passes: [cap u32 | global counters u32 | thr u32 | over u8 | closed u8] x node
+    DevBuf d_bounded;
+    uint64_t cap_key[4] = {~0ull, 0, 0, 0};   // (n_total_objs, num << 32 | den, table version, M) the uploaded capacities belong to
+    uint64_t tab_version = 0;
     unsigned long long *d_scalars = nullptr;   // S_COUNT u64 + error u32
     unsigned long long *h_scalars = nullptr;   // pinned mirror
 
@@ -227,7 +233,7 @@ void build_tab(rio_placement *h, TabBufs &tb, const std::vector<uint8_t> *closed
     for (size_t q = 0; q < live.size(); q++) {
         const NodeInfo &ni = h->nodes[live[q].idx];
         recs[q] = NodeRec{(uint32_t)ni.seed, live[q].idx, (uint32_t)(ni.seed >> 32) | 1u, (uint32_t)ni.seed2};
-        if (q == 0 || live[q].invw != live[q - 1].invw) classes.push_back(ClassRec{(uint32_t)q, live[q].invw});
+        if (q == 0 || live[q].invw != live[q - 1].invw || (h->dev_table_flags & RIO_DEV_SPLIT_CLASSES)) classes.push_back(ClassRec{(uint32_t)q, live[q].invw});
     }
     const uint32_t n_classes = (uint32_t)classes.size();
     classes.push_back(ClassRec{(uint32_t)live.size(), 0});
@@ -302,7 +308,9 @@ void ensure_tab(rio_placement *h) {
     std::vector<float> fnode((size_t)(n_total ? n_total : 1) * (h->K ? h->K : 1), 0.f);
     for (uint32_t j = 0; j < n_total; j++) {
         const NodeInfo &ni = h->nodes[j];
-        state[j] = (ni.live() ? kNodeLive : 0) | (ni.malformed ? kNodeMalformed : 0);
+        // the per-request policy asks is_active(ip, port) only (storage/mod.rs:102-110): a draining node (active, weight 0) keeps its
+        // objects; weight > 0 matters to the solver alone (live[], the class table, the trie)
+        state[j] = ((ni.active && !ni.malformed) ? kNodeLive : 0) | (ni.malformed ? kNodeMalformed : 0);
         live[j] = ni.live() ? 1u : 0u;
         if (h->K && ni.feat.size() == h->K) std::copy(ni.feat.begin(), ni.feat.end(), fnode.begin() + (size_t)j * h->K);   // others keep zeros
     }
@@ -340,6 +348,7 @@ void ensure_tab(rio_placement *h) {
     }
     CUDA_TRY(cudaStreamSynchronize(st));
     h->tab_dirty = false;
+    h->tab_version++;
 }
 
 // ---- directory sizing ---------------------------------------------------------------------------------------
@@ -365,7 +374,13 @@ void dir_reserve(rio_placement *h, uint64_t n_more) {
     const uint64_t need = h->dir_keys + h->dir_keys_pending + n_more;
     if (need * 10 <= h->dir_cap * 7) return;
     if (h->dir_keys_pending) { reconcile_dir_keys(h); if ((h->dir_keys + n_more) * 10 <= h->dir_cap * 7) return; }
-    const uint64_t new_cap = pow2_at_least(std::max<uint64_t>((h->dir_keys + n_more) * 2, 1024));
+    // Removed / cleaned keys stay in the table as tombstones (they keep probe chains intact) and are counted in dir_keys; the
+    // rehash drops them, so the new table is sized for the keys that are actually placed: under create/remove churn with a
+    // constant live count this is a same-size compaction, not a doubling.
+    zero_scalar(h, S_PLACED);
+    launch_dir_count(h->L(), h->dir, h->d_scalars + S_PLACED, nullptr, 0);
+    const uint64_t placed = read_scalar(h, S_PLACED);
+    const uint64_t new_cap = pow2_at_least(std::max<uint64_t>((placed + n_more) * 2, 1024));
     DirDev nd{};
     dir_alloc(h, new_cap, nd);
     CUDA_TRY(cudaMemsetAsync(h->d_scalars + S_NEWKEYS, 0, 8, h->stream));
@@ -434,7 +449,8 @@ uint32_t capacity_of(uint64_t n_total, uint32_t w, uint64_t w_sum, uint32_t num,
 }
 
 // host keys -> device, chunk-pipelined on three streams so H2D, the score grid and D2H overlap (e2e path)
-void assign_host_pipelined(rio_placement *h, const uint64_t *keys, const float *feats, size_t n, uint32_t *out) {
+void assign_host_pipelined(rio_placement *h, const uint64_t *keys, const float *feats, size_t n, uint32_t *out, uint32_t *d_counters = nullptr,
+                           bool final_sync = true) {
     ensure_tab(h);
     if (feats) REQUIRE(h->K > 0, "assign with object features needs node features (set_nodes feats)");
     // chunks of two full kernel waves (about 0.9 M objects on 148 SMs): whole waves leave no tail, small chunks keep the
@@ -456,14 +472,91 @@ void assign_host_pipelined(rio_placement *h, const uint64_t *keys, const float *
         if (feats)
             run_affinity(h, h->s_feats.as<float>() + lo * h->K, m, h->s_idx.as<uint32_t>() + lo, nullptr, nullptr);
         else
-            run_assign(h, h->solver, h->tabs, h->s_keys.as<uint64_t>() + lo, m, h->s_idx.as<uint32_t>() + lo, nullptr, nullptr, 0);
+            run_assign(h, h->solver, h->tabs, h->s_keys.as<uint64_t>() + lo, m, h->s_idx.as<uint32_t>() + lo, d_counters, nullptr, 0);
         CUDA_TRY(cudaEventRecord(h->ev_pipe[2], h->stream));
         CUDA_TRY(cudaStreamWaitEvent(h->d2h_stream, h->ev_pipe[2], 0));
         CUDA_TRY(cudaMemcpyAsync(out + lo, h->s_idx.as<uint32_t>() + lo, m * 4, cudaMemcpyDeviceToHost, h->d2h_stream));
     }
+    if (!final_sync) return;   // the caller still has work for the main stream (capacity check) while the last D2H is in flight
     CUDA_TRY(cudaEventRecord(h->ev_pipe[3], h->d2h_stream));
     CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_pipe[3], 0));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+}
+
+// ---- bounded-load rounds over a device-resident (keys, idx, counters) triple ------------------------------------
+// Pass 0 = plain assignment with the fused histogram.  After every pass ONE small kernel does the counter exchange (peer
+// memory, world > 1) and the capacity check on the device and leaves two words in mapped pinned memory; the host reads those
+// after the stream synchronises.  Only when a node is over capacity (rare at the default factor 1.25) do the thresholds get
+// used by the spill selection and the closed set come back to the host for the masked table of the next pass.
+struct BoundedDev { uint32_t *cap, *glob, *thr; uint8_t *over, *closed; };
+BoundedDev bounded_layout(rio_placement *h, uint32_t M) {
+    const size_t m = std::max(M, 1u);
+    h->d_bounded.ensure(m * 14 + 64, h->stream);
+    BoundedDev b;
+    b.cap = h->d_bounded.as<uint32_t>();
+    b.glob = b.cap + m;
+    b.thr = b.glob + m;
+    b.over = reinterpret_cast<uint8_t *>(b.thr + m);
+    b.closed = b.over + m;
+    return b;
+}
+
+// one exchange + check; returns {any over, open nodes}
+std::pair<uint32_t, uint32_t> exchange_and_check(rio_placement *h, const uint32_t *d_local, const BoundedDev &b, uint32_t M) {
+    volatile uint32_t *flags = reinterpret_cast<volatile uint32_t *>(h->h_scalars + S_FLAGS);
+    uint32_t *flags_dev = nullptr;
+    CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void **>(&flags_dev), const_cast<uint32_t *>(flags), 0));
+    const uint8_t *state = h->d_node_state.as<uint8_t>();
+    if (h->world > 1 && h->xchg_ready && M <= h->xchg_nodes) {
+        launch_exchange_check(h->L(), d_local, h->xchg_peer, (uint32_t)h->rank, (uint32_t)h->world, M, h->xchg_nodes, ++h->xchg_epoch, b.glob, b.cap, state,
+                              b.closed, b.thr, b.over, flags_dev);
+    } else {
+        const uint32_t *src = d_local;
+        if (h->world > 1 && h->comm) {   // portable path: NCCL all-gather + sum, then the check alone
+            h->s_gather.ensure((size_t)M * 4 * h->world, h->stream);
+            NCCL_TRY(g_nccl.AllGather(d_local, h->s_gather.p, M, kNcclUint32, h->comm, h->stream));
+            launch_sum_gathered(h->L(), h->s_gather.as<uint32_t>(), (uint32_t)h->world, M, b.glob);
+            src = b.glob;
+        }
+        launch_exchange_check(h->L(), src, nullptr, 0, 1, M, 0, 0, b.glob, b.cap, state, b.closed, b.thr, b.over, flags_dev);
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return {flags[0], flags[1]};
+}
+
+uint32_t bounded_rounds(rio_placement *h, const uint64_t *d_keys, uint64_t n, uint32_t *d_idx, uint32_t *d_counters, uint32_t *d_sel, uint32_t M,
+                        uint64_t n_total_objs, uint32_t cap_num, uint32_t cap_den, uint32_t max_rounds, bool first_pass_done) {
+    cudaStream_t st = h->stream;
+    const BoundedDev b = bounded_layout(h, M);
+    const uint64_t key[4] = {n_total_objs, ((uint64_t)cap_num << 32) | cap_den, h->tab_version, M};
+    if (memcmp(key, h->cap_key, sizeof key) != 0) {   // capacities depend only on (N, factor, live weights): upload once per table
+        uint64_t W = 0;
+        for (auto &ni : h->nodes) if (ni.live()) W += ni.weight;
+        std::vector<uint32_t> cap(std::max(M, 1u), 0);
+        for (uint32_t j = 0; j < M && j < h->nodes.size(); j++) if (h->nodes[j].live()) cap[j] = capacity_of(n_total_objs, h->nodes[j].weight, W, cap_num, cap_den);
+        CUDA_TRY(cudaMemcpyAsync(b.cap, cap.data(), (size_t)std::max(M, 1u) * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        memcpy(h->cap_key, key, sizeof key);
+    }
+    CUDA_TRY(cudaMemsetAsync(b.closed, 0, std::max(M, 1u), st));
+    if (!first_pass_done) {
+        CUDA_TRY(cudaMemsetAsync(d_counters, 0, (size_t)std::max(M, 1u) * 4, st));
+        run_assign(h, h->solver, h->tabs, d_keys, n, d_idx, d_counters, nullptr, 0);
+    }
+    uint32_t passes = 1;
+    for (uint32_t r = 1; r < max_rounds; r++) {
+        const auto [any, open] = exchange_and_check(h, d_counters, b, M);                  // the one collective of this pass
+        if (!any || !open) break;
+        zero_scalar(h, S_NSEL);
+        launch_select_spill(h->L(), d_keys, d_idx, n, b.thr, b.over, r, d_sel, h->d_scalars + S_NSEL, d_counters);
+        std::vector<uint8_t> closed(M, 0);
+        CUDA_TRY(cudaMemcpyAsync(closed.data(), b.closed, M, cudaMemcpyDeviceToHost, st));
+        const uint64_t nsel = read_scalar(h, S_NSEL);
+        build_tab(h, h->tabs_masked, &closed);
+        if (nsel) run_assign(h, h->solver, h->tabs_masked, d_keys, n, d_idx, d_counters, d_sel, nsel);
+        passes++;
+    }
+    return passes;
 }
 
 template <class F>
@@ -552,7 +645,8 @@ rio_status rio_cuda_create(const rio_config *cfg, rio_placement **out) {
         CUDA_TRY(cudaMalloc(&sc, (S_COUNT + 1) * 8));
         CUDA_TRY(cudaMemset(sc, 0, (S_COUNT + 1) * 8));
         h->d_scalars = reinterpret_cast<unsigned long long *>(sc);
-        CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&h->h_scalars), (S_COUNT + 1) * 8));
+        CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&h->h_scalars), (S_COUNT + 1) * 8, cudaHostAllocMapped));   // S_FLAGS is written by the device
+        memset(h->h_scalars, 0, (S_COUNT + 1) * 8);
         uint64_t cap = cfg && cfg->struct_size >= sizeof(rio_config) && cfg->directory_capacity ? cfg->directory_capacity : (1ull << 16);
         cap = pow2_at_least(std::max<uint64_t>(cap, 1024));
         dir_alloc(h, cap, h->dir);
@@ -583,7 +677,7 @@ void rio_cuda_destroy(rio_placement *h) {
     }
     DevBuf *bufs[] = {&h->tabs.recs, &h->tabs.classes, &h->tabs.by_idx, &h->tabs_masked.recs, &h->tabs_masked.classes, &h->tabs_masked.by_idx, &h->tabs.trie_blob, &h->tabs_masked.trie_blob,
                       &h->d_node_state, &h->d_live, &h->d_fnode, &h->d_fnode_c, &h->d_fnode_g, &h->d_nidx_map, &h->s_keys, &h->s_idx, &h->s_idx2, &h->s_sel, &h->s_slots, &h->s_keys2, &h->s_feats,
-                      &h->s_packed, &h->s_offsets, &h->s_cost, &h->s_misc, &h->s_flush, &h->s_gather};
+                      &h->s_packed, &h->s_offsets, &h->s_cost, &h->s_misc, &h->s_flush, &h->s_gather, &h->d_bounded};
     for (DevBuf *b : bufs) b->release(h->stream);
     if (h->dir.slots) cudaFreeAsync(h->dir.slots, h->stream);
     cudaStreamSynchronize(h->stream);
@@ -832,6 +926,36 @@ rio_status rio_cuda_assign_batch(rio_placement *h, const uint64_t *keys, const f
     });
 }
 
+rio_status rio_cuda_assign_bounded_batch(rio_placement *h, const uint64_t *keys, size_t n, uint64_t n_total_objs, uint32_t cap_num, uint32_t cap_den,
+                                         uint32_t max_rounds, uint32_t *out_idx, uint32_t *out_passes) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] {
+        if (out_passes) *out_passes = 0;
+        if (!n) return;
+        REQUIRE(keys && out_idx, "null buffer");
+        REQUIRE(cap_den > 0 && max_rounds > 0, "bad capacity factor / rounds");
+        REQUIRE(n < 0xFFFFFFFFull, "batch too large");
+        ensure_tab(h);
+        const uint32_t M = h->tabs.tab.n_total;
+        if (!n_total_objs) n_total_objs = (uint64_t)n * (uint64_t)h->world;
+        h->s_misc.ensure((size_t)std::max(M, 1u) * 4, h->stream);
+        h->s_sel.ensure(n * 4, h->stream);
+        uint32_t *d_cnt = h->s_misc.as<uint32_t>();
+        CUDA_TRY(cudaMemsetAsync(d_cnt, 0, (size_t)std::max(M, 1u) * 4, h->stream));
+        // pass 0: chunk-pipelined H2D / score+histogram / D2H; the exchange + capacity check runs behind the last chunk while its
+        // indices are still crossing PCIe
+        assign_host_pipelined(h, keys, nullptr, n, out_idx, d_cnt, false);
+        const uint32_t passes = bounded_rounds(h, h->s_keys.as<uint64_t>(), n, h->s_idx.as<uint32_t>(), d_cnt, h->s_sel.as<uint32_t>(), M, n_total_objs, cap_num, cap_den,
+                                               max_rounds, true);
+        CUDA_TRY(cudaStreamSynchronize(h->d2h_stream));
+        if (passes > 1) {   // a spill round rewrote some indices after their chunk had left: send the final state again
+            CUDA_TRY(cudaMemcpyAsync(out_idx, h->s_idx.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+            CUDA_TRY(cudaStreamSynchronize(h->stream));
+        }
+        if (out_passes) *out_passes = passes;
+    });
+}
+
 rio_status rio_cuda_assign_batch_dev(rio_placement *h, const uint64_t *d_keys, const float *d_obj_feats, size_t n, uint32_t *d_out_idx) {
     if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
     return guarded(h, [&] {
@@ -901,6 +1025,66 @@ rio_status rio_cuda_place_batch(rio_placement *h, const uint64_t *keys, size_t n
         CUDA_TRY(cudaMemcpyAsync(out_idx, h->s_idx.p, n * 4, cudaMemcpyDeviceToHost, st));
         if (nsel) { reconcile_dir_keys(h); check_device_error(h); } else CUDA_TRY(cudaStreamSynchronize(st));
     });
+}
+
+rio_status rio_cuda_check_address_batch(rio_placement *h, const uint32_t *addr_idx, size_t n, uint32_t self_idx, uint8_t *out_verdict, uint64_t *out_cleaned) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] {
+        if (out_cleaned) *out_cleaned = 0;
+        if (!n) return;
+        REQUIRE(addr_idx && out_verdict, "null buffer");
+        REQUIRE(self_idx < h->nodes.size(), "self_idx is not a known node");
+        const uint32_t n_total = (uint32_t)h->nodes.size();
+        // verdict of every interned address against this server (service.rs:261-298): a table of n_total bytes, built on the host
+        // from the membership view, applied to the batch on the device together with the clean_server scan
+        std::vector<uint8_t> verdict(n_total, RIO_ADDR_DEALLOCATE);
+        for (uint32_t j = 0; j < n_total; j++) {
+            const std::string &a = h->nodes[j].addr;
+            if (j == self_idx) { verdict[j] = RIO_ADDR_LOCAL; continue; }                          // :262-264 (before any format check)
+            const size_t c = a.find(':');
+            if (c == std::string::npos) { verdict[j] = RIO_ADDR_MALFORMED; continue; }              // :272-278 "Missing PORT"
+            const size_t c2 = a.find(':', c + 1);                                                    // split(':'): ip = piece 0, port = piece 1
+            bool active = h->nodes[j].active;
+            if (c2 != std::string::npos) {   // a third piece: is_active is asked about "ip:port" of the first two
+                auto it = h->node_index.find(a.substr(0, c2));
+                active = it != h->node_index.end() && h->nodes[it->second].active;
+            }
+            verdict[j] = active ? RIO_ADDR_REDIRECT : RIO_ADDR_DEALLOCATE;                          // :280-297
+        }
+        cudaStream_t st = h->stream;
+        h->s_idx.ensure(n * 4, st);
+        h->s_idx2.ensure(n, st);
+        h->s_misc.ensure((size_t)n_total * 2, st);
+        uint8_t *d_verdict_tab = h->s_misc.as<uint8_t>(), *d_dead = d_verdict_tab + n_total;
+        CUDA_TRY(cudaMemcpyAsync(h->s_idx.p, addr_idx, n * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_verdict_tab, verdict.data(), n_total, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemsetAsync(d_dead, 0, n_total, st));
+        zero_scalar(h, S_NSEL);
+        zero_scalar(h, S_MOVED);
+        launch_check_address(h->L(), h->s_idx.as<uint32_t>(), n, d_verdict_tab, n_total, h->s_idx2.as<uint8_t>(), d_dead, h->d_scalars + S_NSEL);
+        CUDA_TRY(cudaMemcpyAsync(out_verdict, h->s_idx2.p, n, cudaMemcpyDeviceToHost, st));
+        const uint64_t n_dead = read_scalar(h, S_NSEL);
+        if (n_dead) {   // clean_server for every non-active address that was met (service.rs:291-296): one scan for all of them
+            launch_dir_clean_flagged(h->L(), h->dir, d_dead, n_total, h->d_scalars + S_MOVED);
+            const uint64_t cleaned = read_scalar(h, S_MOVED);
+            if (out_cleaned) *out_cleaned = cleaned;
+        }
+    });
+}
+
+rio_status rio_dev_set_node_seed(rio_placement *h, uint32_t idx, uint64_t seed) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] {
+        REQUIRE(idx < h->nodes.size(), "node index out of range");
+        h->nodes[idx].seed = seed;
+        h->nodes[idx].seed2 = mix64(seed ^ kSaltNode2);
+        h->tab_dirty = true;
+    });
+}
+
+rio_status rio_dev_set_table_options(rio_placement *h, uint32_t flags) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] { h->dev_table_flags = flags; h->tab_dirty = true; });
 }
 
 rio_status rio_cuda_rebalance(rio_placement *h, uint32_t event, uint32_t idx, uint64_t *out_moved) {
@@ -1010,46 +1194,12 @@ rio_status rio_cuda_set_assign_bounded(rio_objset *s, uint64_t n_total_objs, uin
         REQUIRE(cap_den > 0 && max_rounds > 0, "bad capacity factor / rounds");
         ensure_tab(h);
         set_ensure_counters(s);
-        const uint32_t M = s->counters_n;
         if (!n_total_objs) n_total_objs = s->n * (uint64_t)h->world;
-        uint64_t W = 0;
-        for (auto &ni : h->nodes) if (ni.live()) W += ni.weight;
-        std::vector<uint32_t> cap(M, 0), thr(M, 0), cnt(M, 0);
-        std::vector<uint8_t> over(M, 0), closed(M, 0);
-        for (uint32_t j = 0; j < M; j++) if (h->nodes[j].live()) cap[j] = capacity_of(n_total_objs, h->nodes[j].weight, W, cap_num, cap_den);
-        cudaStream_t st = h->stream;
-        h->s_misc.ensure((size_t)std::max(M, 1u) * 9, st);   // [global counters u32 | thr u32 | over u8]
-        uint32_t *d_glob = h->s_misc.as<uint32_t>();
-        uint32_t *d_thr = d_glob + M;
-        uint8_t *d_over = reinterpret_cast<uint8_t *>(d_thr + M);
-        CUDA_TRY(cudaMemsetAsync(s->counters.p, 0, (size_t)std::max(M, 1u) * 4, st));
-        run_assign(h, h->solver, h->tabs, s->keys.as<uint64_t>(), s->n, s->idx.as<uint32_t>(), s->counters.as<uint32_t>(), nullptr, 0);
-        uint32_t passes = 1;
-        for (uint32_t r = 1; r < max_rounds; r++) {
-            exchange_counters(h, s->counters.as<uint32_t>(), d_glob, M);                  // the one collective of this pass
-            if (M) CUDA_TRY(cudaMemcpyAsync(cnt.data(), d_glob, (size_t)M * 4, cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaStreamSynchronize(st));
-            bool any = false; uint32_t open = 0;
-            for (uint32_t j = 0; j < M; j++) {
-                over[j] = h->nodes[j].live() && cnt[j] > cap[j];
-                thr[j] = 0;
-                if (over[j]) { any = true; closed[j] = 1; thr[j] = (uint32_t)((((uint64_t)(cnt[j] - cap[j])) << 32) / cnt[j]); }
-            }
-            for (uint32_t j = 0; j < M; j++) open += h->nodes[j].live() && !closed[j];
-            if (!any || !open) break;
-            CUDA_TRY(cudaMemcpyAsync(d_thr, thr.data(), (size_t)M * 4, cudaMemcpyHostToDevice, st));
-            CUDA_TRY(cudaMemcpyAsync(d_over, over.data(), M, cudaMemcpyHostToDevice, st));
-            zero_scalar(h, S_NSEL);
-            launch_select_spill(h->L(), s->keys.as<uint64_t>(), s->idx.as<uint32_t>(), s->n, d_thr, d_over, r, s->sel.as<uint32_t>(), h->d_scalars + S_NSEL,
-                                s->counters.as<uint32_t>());
-            const uint64_t nsel = read_scalar(h, S_NSEL);
-            build_tab(h, h->tabs_masked, &closed);
-            if (nsel) run_assign(h, h->solver, h->tabs_masked, s->keys.as<uint64_t>(), s->n, s->idx.as<uint32_t>(), s->counters.as<uint32_t>(), s->sel.as<uint32_t>(), nsel);
-            passes++;
-        }
+        const uint32_t passes = bounded_rounds(h, s->keys.as<uint64_t>(), s->n, s->idx.as<uint32_t>(), s->counters.as<uint32_t>(), s->sel.as<uint32_t>(), s->counters_n,
+                                               n_total_objs, cap_num, cap_den, max_rounds, false);
         s->assigned = true;
         if (out_passes) *out_passes = passes;
-        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
     });
 }
 

@@ -550,6 +550,7 @@ void launch_assign_hrw(const Launch &L, const uint64_t *d_keys, uint64_t n, cons
                                                                                                                   d_counters, d_sel, chunk_cap, hist_bins); \
         } while (0)
         switch (tune) {
+#ifdef RIO_ASSIGN_TUNING   // A/B tuning points (RIO_BUILD_TUNING=1): not in the shipped library
             case 430: RIO_LAUNCH_V2(4, 3, 8); break;
             case 431: RIO_LAUNCH_V2(4, 3, 16); break;
             case 432: RIO_LAUNCH_V2(4, 3, 32); break;
@@ -562,6 +563,7 @@ void launch_assign_hrw(const Launch &L, const uint64_t *d_keys, uint64_t n, cons
             case 332: RIO_LAUNCH_V2(3, 3, 32); break;
             case 622: RIO_LAUNCH_V2(6, 2, 32); break;
             case 522: RIO_LAUNCH_V2(5, 2, 32); break;
+#endif
             case 532: default: RIO_LAUNCH_V2(5, 3, 32); break;
         }
 #undef RIO_LAUNCH_V2

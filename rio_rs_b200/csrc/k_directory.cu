@@ -198,11 +198,16 @@ k_dir_count(DirDev dir, unsigned long long *placed, uint32_t *counters, uint32_t
 // JOIN(new): an object moves iff the new node beats its incumbent under the spec order (score, ~u, j); both
 // candidates are one pair hash each (the incumbent's is recomputed from (key, idx) instead of being stored, so
 // the stream is 12 B/object for a dense set, 16 B/slot for the directory).  by_idx[] gives {s0, invw, s2}.
-__device__ __forceinline__ bool join_wins(uint64_t key, uint32_t cur, uint32_t new_idx, const uint4 nn, const uint4 *by_idx) {
+// Returns the node the object belongs on after the join: new_idx if it beats the incumbent, the incumbent otherwise; an
+// incumbent that is not live (recorded on an inactive / zero-weight / never-live address: update() may record anything) is
+// re-placed by the full rendezvous over the live table, exactly what a fresh assignment would do -- not handed to the joiner.
+__device__ uint32_t hrw_scalar(uint64_t key, const NodeTabDev &tab);
+__device__ __forceinline__ bool join_wins(uint64_t key, uint32_t cur, uint32_t new_idx, const uint4 nn, const uint4 *by_idx, bool *incumbent_dead) {
     const ObjHash o = obj_hash(key);
     const uint32_t un = pair_hash(o, nn.x, nn.z, nn.w);
     const uint4 c = by_idx[cur];   // shared memory (staged) or global
-    if (c.y == 0) return true;   // incumbent is not live any more
+    *incumbent_dead = c.y == 0;
+    if (c.y == 0) return false;
     const uint32_t uc = pair_hash(o, c.x, c.z, c.w);
     // cheap bracket first: E(u) lies in [clz(u) << 26, (clz(u)+1) << 26], so most comparisons (the new node wins only
     // ~w/W of the time) are decided without evaluating the log polynomial at all
@@ -235,8 +240,12 @@ k_rebalance_join(const uint64_t *__restrict__ keys, uint32_t *__restrict__ idx, 
         if (i < n) {
             const uint32_t cur = idx[i];
             if (cur != new_idx && cur < tab.n_total && nn.y) {
-                mv = join_wins(__ldg(keys + i), cur, new_idx, nn, by_idx);
-                if (mv) { idx[i] = new_idx; if (counters) { atomicSub(&counters[cur], 1u); atomicAdd(&counters[new_idx], 1u); } }
+                bool dead;
+                const uint64_t key = __ldg(keys + i);
+                mv = join_wins(key, cur, new_idx, nn, by_idx, &dead);
+                uint32_t to = new_idx;
+                if (dead) { to = hrw_scalar(key, tab); mv = to != cur; }   // rare: incumbent not live
+                if (mv) { idx[i] = to; if (counters) { atomicSub(&counters[cur], 1u); if (to != kNone) atomicAdd(&counters[to], 1u); } }
             }
         }
         warp_add(moved, mv);
@@ -256,8 +265,11 @@ k_dir_rebalance_join(DirDev dir, NodeTabDev tab, uint32_t new_idx, unsigned long
             const uint4 v = slots[i];
             const unsigned long long key = ((unsigned long long)v.y << 32) | v.x;
             if (key != kEmptyKey && v.z != kNone && v.z != new_idx && v.z < tab.n_total && nn.y) {
-                mv = join_wins(key, v.z, new_idx, nn, by_idx);
-                if (mv) reinterpret_cast<uint32_t *>(&dir.slots[i].val)[0] = new_idx;
+                bool dead;
+                mv = join_wins(key, v.z, new_idx, nn, by_idx, &dead);
+                uint32_t to = new_idx;
+                if (dead) { to = hrw_scalar(key, tab); mv = to != v.z; }
+                if (mv) reinterpret_cast<uint32_t *>(&dir.slots[i].val)[0] = to;
             }
         }
         warp_add(moved, mv);
@@ -383,6 +395,24 @@ k_classify(const uint32_t *__restrict__ cur, uint64_t n, const uint8_t *__restri
     }
 }
 
+// Service::check_address_mismatch, batched (service.rs:261-298): the verdict per interned address comes in a byte table
+__global__ void __launch_bounds__(256)
+k_check_address(const uint32_t *__restrict__ idx, uint64_t n, const uint8_t *__restrict__ verdict_tab, uint32_t n_total, uint8_t *__restrict__ out,
+                uint8_t *__restrict__ dead_flag, unsigned long long *ndead) {
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = base + threadIdx.x;
+        bool dead = false;
+        if (i < n) {
+            const uint32_t j = __ldg(idx + i);
+            const uint8_t v = j < n_total ? __ldg(verdict_tab + j) : (uint8_t)3;
+            out[i] = v;
+            dead = v == 2;
+            if (dead) dead_flag[j] = 1;
+        }
+        warp_add(ndead, dead);
+    }
+}
+
 __global__ void k_scatter_const(uint32_t *__restrict__ out, const uint32_t *__restrict__ sel, uint64_t n_sel, uint32_t v) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_sel; i += (uint64_t)gridDim.x * blockDim.x) out[sel[i]] = v;
 }
@@ -431,7 +461,72 @@ k_exchange_p2p(const uint32_t *__restrict__ local, XchgPeers peers, uint32_t ran
     }
 }
 
+// The counter exchange AND the bounded-load capacity check of a pass as one single-CTA kernel: exchange as
+// above (skipped when world == 1), then per node  over = live && count > cap,  thr = floor(2^32 (count - cap) / count),
+// closed |= over, and two words for the host in mapped pinned memory: {any node over, live nodes still open}.  The host
+// reads 8 bytes after the stream synchronises; the M-wide counter vector never crosses PCIe unless a spill round follows.
+__global__ void __launch_bounds__(1024)
+k_exchange_check(const uint32_t *__restrict__ local, XchgPeers peers, uint32_t rank, uint32_t world, uint32_t M, uint32_t max_nodes, uint32_t epoch,
+                 uint32_t *__restrict__ out_global, const uint32_t *__restrict__ cap, const uint8_t *__restrict__ node_state, uint8_t *__restrict__ closed,
+                 uint32_t *__restrict__ thr, uint8_t *__restrict__ over, volatile uint32_t *host_flags) {
+    __shared__ uint32_t s_any, s_open;
+    if (threadIdx.x == 0) { s_any = 0; s_open = 0; }
+    if (world > 1) {
+        const size_t slot_words = (size_t)2 * world * max_nodes;
+        const size_t par = (size_t)(epoch & 1u) * world * max_nodes;
+        for (uint32_t p = 0; p < world; p++) {
+            uint32_t *dst = peers.win[p] + par + (size_t)rank * max_nodes;
+            for (uint32_t j = threadIdx.x; j < M; j += blockDim.x) dst[j] = local[j];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < world) {
+            uint32_t *flag = peers.win[threadIdx.x] + slot_words + rank;
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+            const uint32_t *mine = peers.win[rank] + slot_words + threadIdx.x;
+            uint32_t v;
+            do { asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory"); } while ((int32_t)(v - epoch) < 0);
+        }
+        __syncthreads();
+        const uint32_t *src = peers.win[rank] + par;
+        for (uint32_t j = threadIdx.x; j < M; j += blockDim.x) {
+            uint32_t sum = 0;
+            for (uint32_t r = 0; r < world; r++) sum += src[(size_t)r * max_nodes + j];
+            out_global[j] = sum;
+        }
+    } else {
+        __syncthreads();
+        if (local != out_global)
+            for (uint32_t j = threadIdx.x; j < M; j += blockDim.x) out_global[j] = local[j];
+    }
+    uint32_t my_any = 0, my_open = 0;
+    for (uint32_t j = threadIdx.x; j < M; j += blockDim.x) {      // same thread wrote out_global[j] above
+        const bool live = node_state[j] & kNodeLive;
+        const uint32_t c = out_global[j], cp = cap[j];
+        const bool ov = live && c > cp;
+        over[j] = ov;
+        thr[j] = ov ? (uint32_t)((((unsigned long long)(c - cp)) << 32) / c) : 0u;
+        if (ov) closed[j] = 1;
+        my_any |= ov;
+        my_open += live && !closed[j];
+    }
+    if (my_any) atomicOr(&s_any, 1u);
+    if (my_open) atomicAdd(&s_open, my_open);
+    __syncthreads();
+    if (threadIdx.x == 0) { host_flags[0] = s_any; host_flags[1] = s_open; __threadfence_system(); }
+}
+
 }  // namespace
+
+void launch_exchange_check(const Launch &L, const uint32_t *d_local, uint32_t *const *peer_windows, uint32_t rank, uint32_t world, uint32_t M, uint32_t max_nodes,
+                           uint32_t epoch, uint32_t *d_out_global, const uint32_t *d_cap, const uint8_t *d_node_state, uint8_t *d_closed, uint32_t *d_thr,
+                           uint8_t *d_over, uint32_t *host_flags_mapped) {
+    XchgPeers P{};
+    if (peer_windows) for (uint32_t p = 0; p < world && p < 16; p++) P.win[p] = peer_windows[p];
+    k_exchange_check<<<1, 1024, 0, L.stream>>>(d_local, P, rank, peer_windows ? world : 1u, M, max_nodes, epoch, d_out_global, d_cap, d_node_state, d_closed, d_thr,
+                                               d_over, host_flags_mapped);
+    RIO_COUNT_LAUNCH(L);
+}
 
 void launch_exchange_p2p(const Launch &L, const uint32_t *d_local, uint32_t *const *peer_windows, uint32_t rank, uint32_t world, uint32_t M, uint32_t max_nodes,
                          uint32_t epoch, uint32_t *d_out_global) {
@@ -509,6 +604,12 @@ void launch_classify(const Launch &L, const uint32_t *d_cur, uint64_t n, const u
                      unsigned long long *d_nsel, uint8_t *d_dead_flag) {
     if (!n) return;
     k_classify<<<grid_for(n, 256, L.sm_count, 8), 256, 0, L.stream>>>(d_cur, n, d_node_state, n_total, d_sel, d_nsel, d_dead_flag);
+    RIO_COUNT_LAUNCH(L);
+}
+void launch_check_address(const Launch &L, const uint32_t *d_idx, uint64_t n, const uint8_t *d_verdict_tab, uint32_t n_total, uint8_t *d_out, uint8_t *d_dead_flag,
+                          unsigned long long *d_ndead) {
+    if (!n) return;
+    k_check_address<<<grid_for(n, 256, L.sm_count, 8), 256, 0, L.stream>>>(d_idx, n, d_verdict_tab, n_total, d_out, d_dead_flag, d_ndead);
     RIO_COUNT_LAUNCH(L);
 }
 void launch_scatter_const(const Launch &L, uint32_t *d_out, const uint32_t *d_sel, uint64_t n_sel, uint32_t v) {

@@ -112,11 +112,19 @@ void launch_dir_reassign_trie(const Launch &L, const DirDev &dir, const TrieDev 
 // need[i] = 1 if object must be (re)placed; dead_flag[node] = 1 for inactive well-formed nodes that were hit
 void launch_classify(const Launch &L, const uint32_t *d_cur, uint64_t n, const uint8_t *d_node_state, uint32_t n_total, uint32_t *d_sel,
                      unsigned long long *d_nsel, uint8_t *d_dead_flag);
+// check_address_mismatch for a batch: verdict[i] = verdict_tab[idx[i]] (RIO_ADDR_*; out-of-range index -> MALFORMED); nodes that
+// drew DEALLOCATE are flagged for the clean_server scan and counted
+void launch_check_address(const Launch &L, const uint32_t *d_idx, uint64_t n, const uint8_t *d_verdict_tab, uint32_t n_total, uint8_t *d_out, uint8_t *d_dead_flag,
+                          unsigned long long *d_ndead);
 void launch_scatter_const(const Launch &L, uint32_t *d_out, const uint32_t *d_sel, uint64_t n_sel, uint32_t v);
 void launch_gather_keys(const Launch &L, const uint64_t *d_keys, const uint32_t *d_sel, uint64_t n_sel, uint64_t *d_out_keys, const uint32_t *d_idx,
                         uint32_t *d_out_idx);
 void launch_exchange_p2p(const Launch &L, const uint32_t *d_local, uint32_t *const *peer_windows, uint32_t rank, uint32_t world, uint32_t M, uint32_t max_nodes,
                          uint32_t epoch, uint32_t *d_out_global);
+// exchange (world > 1, peer windows given) + bounded-load capacity check in one launch; host_flags_mapped = 2 u32 in mapped pinned memory
+void launch_exchange_check(const Launch &L, const uint32_t *d_local, uint32_t *const *peer_windows /*nullable*/, uint32_t rank, uint32_t world, uint32_t M,
+                           uint32_t max_nodes, uint32_t epoch, uint32_t *d_out_global, const uint32_t *d_cap, const uint8_t *d_node_state, uint8_t *d_closed,
+                           uint32_t *d_thr, uint8_t *d_over, uint32_t *host_flags_mapped);
 void launch_sum_gathered(const Launch &L, const uint32_t *d_gathered, uint32_t world, uint32_t M, uint32_t *d_out);
 void launch_l2_flush(const Launch &L, uint32_t *d_buf, uint64_t n_words, uint32_t v);
 

@@ -237,6 +237,15 @@ class GpuObjectPlacement:
         self._ck(self.L.rio_cuda_assign_batch(self.h, _ptr(keys), _ptr(obj_feats), n, _ptr(out)))
         return out
 
+    def assign_bounded_batch(self, keys, n_total=0, cap_num=5, cap_den=4, max_rounds=4, out=None):
+        """assign_batch + bounded-load rounds for host buffers; returns (indices, passes)."""
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        if out is None:
+            out = np.empty(len(keys), dtype=np.uint32)
+        passes = C.c_uint32(0)
+        self._ck(self.L.rio_cuda_assign_bounded_batch(self.h, _ptr(keys), len(keys), n_total, cap_num, cap_den, max_rounds, _ptr(out), C.byref(passes)))
+        return out, passes.value
+
     def place_batch(self, keys, policy="hrw", self_address=None):
         keys = np.ascontiguousarray(keys, dtype=np.uint64)
         out = np.empty(len(keys), dtype=np.uint32)
@@ -248,6 +257,29 @@ class GpuObjectPlacement:
                 raise Unknown("self_address is not a known node")
         self._ck(self.L.rio_cuda_place_batch(self.h, _ptr(keys), len(keys), pol, self_idx, _ptr(out)))
         return out
+
+    def check_address_batch(self, addr_idx, self_address):
+        """Service::check_address_mismatch for a batch (service.rs:261-298) -> (verdicts u8[n] of N.ADDR_*, entries cleaned)."""
+        addr_idx = np.ascontiguousarray(addr_idx, dtype=np.uint32)
+        self_idx = self.node_index(self_address)
+        if self_idx is None:
+            raise Unknown("self_address is not a known node")
+        out = np.empty(len(addr_idx), dtype=np.uint8)
+        cleaned = C.c_uint64(0)
+        self._ck(self.L.rio_cuda_check_address_batch(self.h, _ptr(addr_idx), len(addr_idx), self_idx, _ptr(out), C.byref(cleaned)))
+        return out, cleaned.value
+
+    def check_address_mismatch(self, self_address, server_address):
+        """Per-request form with the reference's signature: -> N.ADDR_LOCAL (Ok) | ADDR_REDIRECT | ADDR_DEALLOCATE | ADDR_MALFORMED."""
+        v, _ = self.check_address_batch([self.node_intern(server_address)], self_address)
+        return int(v[0])
+
+    # ---- test hooks (include/rio_cuda_dev.h) ------------------------------------------------------------------
+    def dev_set_node_seed(self, idx, seed):
+        self._ck(self.L.rio_dev_set_node_seed(self.h, idx, int(seed)))
+
+    def dev_set_table_options(self, flags):
+        self._ck(self.L.rio_dev_set_table_options(self.h, flags))
 
     def rebalance(self, event, idx):
         m = C.c_uint64(0)

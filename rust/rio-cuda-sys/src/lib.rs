@@ -57,6 +57,8 @@ extern "C" {
     pub fn rio_cuda_node_intern(h: *mut rio_placement, address: *const c_char, out_idx: *mut u32) -> rio_status;
     pub fn rio_cuda_node_address(h: *mut rio_placement, idx: u32, buf: *mut c_char, cap: size_t, out_len: *mut size_t) -> rio_status;
     pub fn rio_cuda_node_count(h: *mut rio_placement, out_total: *mut u32, out_live: *mut u32) -> rio_status;
+    pub fn rio_cuda_assign_bounded_batch(h: *mut rio_placement, keys: *const u64, n: usize, n_total: u64, cap_num: u32, cap_den: u32, max_rounds: u32, out_idx: *mut u32, out_passes: *mut u32) -> rio_status;
+    pub fn rio_cuda_check_address_batch(h: *mut rio_placement, addr_idx: *const u32, n: usize, self_idx: u32, out_verdict: *mut u8, out_cleaned: *mut u64) -> rio_status;
     pub fn rio_cuda_set_solver(h: *mut rio_placement, solver: u32, trie_bits: u32) -> rio_status;
     pub fn rio_cuda_get_solver(h: *mut rio_placement, solver: *mut u32, trie_bits: *mut u32) -> rio_status;
 
@@ -75,7 +77,6 @@ extern "C" {
     pub fn rio_cuda_set_create(h: *mut rio_placement, capacity: u64, out: *mut *mut rio_objset) -> rio_status;
     pub fn rio_cuda_set_destroy(s: *mut rio_objset);
     pub fn rio_cuda_set_load_keys(s: *mut rio_objset, keys: *const u64, n: u64) -> rio_status;
-    pub fn rio_cuda_set_synth_keys(s: *mut rio_objset, first: u64, n: u64, seed: u64) -> rio_status;
     pub fn rio_cuda_set_load_feats(s: *mut rio_objset, feats: *const f32, k: u32) -> rio_status;
     pub fn rio_cuda_set_assign(s: *mut rio_objset, use_affinity: u32) -> rio_status;
     pub fn rio_cuda_set_assign_bounded(s: *mut rio_objset, n_total: u64, cap_num: u32, cap_den: u32, max_rounds: u32, out_passes: *mut u32) -> rio_status;
@@ -101,11 +102,6 @@ extern "C" {
     pub fn rio_cuda_assign_batch_dev(h: *mut rio_placement, d_keys: *const u64, d_obj_feats: *const f32, n: size_t, d_out_idx: *mut u32) -> rio_status;
     pub fn rio_cuda_lookup_batch_dev(h: *mut rio_placement, d_keys: *const u64, n: size_t, d_out_idx: *mut u32) -> rio_status;
     pub fn rio_cuda_upsert_batch_dev(h: *mut rio_placement, d_keys: *const u64, d_idx: *const u32, n: size_t) -> rio_status;
-    pub fn rio_cuda_flush_l2(h: *mut rio_placement) -> rio_status;
-    pub fn rio_cuda_event_record(h: *mut rio_placement, slot: u32) -> rio_status;
-    pub fn rio_cuda_event_elapsed_ms(h: *mut rio_placement, a: u32, b: u32, out_ms: *mut f32) -> rio_status;
-    pub fn rio_cuda_bench_mix_rate(h: *mut rio_placement, iters: u32, out_pairs_per_s: *mut f64) -> rio_status;
-    pub fn rio_cuda_launch_count(h: *mut rio_placement, out: *mut u64) -> rio_status;
 
     pub fn rio_cuda_resolver_create(h: *mut rio_placement, policy: u32, self_idx: u32, max_batch: u32, max_wait_us: u32, out: *mut *mut rio_resolver) -> rio_status;
     pub fn rio_cuda_resolver_destroy(r: *mut rio_resolver);

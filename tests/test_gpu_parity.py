@@ -622,3 +622,109 @@ def test_client_first_hop_reaches_the_owner_without_redirect(gp, oracle):
     w2[9] = 0
     fh.set_active_servers(addrs, w2)
     assert (fh.first_hop_batch(keys) == p.lookup_many(keys)).all()
+
+
+# ---- the second half of the per-request policy (service.rs:261-298) ------------------------------------------------
+def test_check_address_mismatch_matches_service_model(gp, oracle):
+    """Service::call runs get_or_create_placement then check_address_mismatch (service.rs:62-70); both halves batched,
+    against the restated reference after membership changes: Ok / Redirect / clean_server + DeallocateServiceObject /
+    Unknown(malformed), including the directory state the clean_server side effect leaves behind."""
+    from rio_rs_b200 import _native as N
+
+    p, m = provider(gp), oracle.DirectoryModel()
+    addrs = ["0.0.0.0:%d" % (5000 + j) for j in range(6)]
+    p.set_nodes(addrs)
+    for a in addrs:
+        ip, port = a.split(":")
+        m.member_push(ip, port, True)
+    ids = [("MockService", str(i)) for i in range(3000)]
+    keys = np.array([oracle.object_key(t, i) for t, i in ids], dtype=np.uint64)
+    # objects land on all six servers (each batch is resolved by "its" server, the reference's first-claim rule)
+    for me in range(6):
+        sel = list(range(me * 500, (me + 1) * 500))
+        got = p.place_batch(keys[sel], "self", addrs[me])
+        assert [p.node_address(int(g)) for g in got] == [m.get_or_create_placement(addrs[me], *ids[s]) for s in sel]
+    # two servers die, one is removed from the membership altogether
+    p.node_set_active(1, False)
+    m.member_set_active("0.0.0.0", "5001", False)
+    p.node_set_active(4, False)
+    m.member_remove("0.0.0.0", "5004")
+    # a request batch arrives at server 2 carrying the owners the directory recorded BEFORE the failure (the window between
+    # the two calls of Service::call); the verdict and the clean_server side effect must match, id for id
+    owner = p.lookup_many(keys)
+    verdict, cleaned = p.check_address_batch(owner, addrs[2])
+    want = [m.check_address_mismatch(addrs[2], p.node_address(int(o))) for o in owner]
+    assert verdict.tolist() == want
+    assert set(want) == {N.ADDR_LOCAL, N.ADDR_REDIRECT, N.ADDR_DEALLOCATE}
+    assert cleaned == 1000                                         # every object of the two dead servers was unassigned
+    for s in range(0, 3000, 3):
+        assert p.lookup(gp.ObjectId(*ids[s])) == m.lookup(*ids[s])
+    assert p.directory_len()[0] == len(m)
+    # per-request form, malformed and three-piece addresses (split(':') keeps the first two pieces)
+    for addr in ("garbage", "0.0.0.0:5003:x", "0.0.0.0:5001:x", "7.7.7.7:1", addrs[2], addrs[3]):
+        p.update(gp.ObjectPlacementItem(gp.ObjectId("E", addr), addr))
+        m.update("E", addr, addr)
+        assert p.check_address_mismatch(addrs[2], addr) == m.check_address_mismatch(addrs[2], addr), addr
+        assert p.lookup(gp.ObjectId("E", addr)) == m.lookup("E", addr), addr
+    assert p.check_address_mismatch("0.0.0.0:5003", "0.0.0.0:5003") == N.ADDR_LOCAL
+
+
+def test_draining_node_keeps_its_objects(gp, oracle):
+    """is_active looks at the membership flag only (storage/mod.rs:102-110): an active node of weight 0 is not a solver target
+    but objects recorded on it are NOT cleaned by the policy."""
+    p = provider(gp)
+    addrs, seeds, w = oracle.synth_nodes(8)
+    p.set_nodes(addrs, w)
+    keys = oracle.synth_keys(4000, 2)
+    owner = p.place_batch(keys, "hrw")
+    w2 = w.copy()
+    w2[3] = 0
+    p.set_nodes(addrs, w2)                                       # node 3 drains: still active, no longer a target
+    assert (p.place_batch(keys, "hrw") == owner).all()           # nothing is re-placed, nothing is cleaned
+    fresh = oracle.synth_keys(4000, 3)
+    assert (p.place_batch(fresh, "hrw") == oracle.assign_hrw(fresh, seeds, w2)).all() and (p.place_batch(fresh, "hrw") != 3).all()
+
+
+# ---- exact ties (DESIGN.md 3.4 tie rules), forced with duplicated node seeds through the dev hook -------------------
+@pytest.mark.parametrize("variant", ["2", "1"])
+@pytest.mark.parametrize("mode", ["within_group", "across_groups", "across_classes", "across_classes_chunked"])
+def test_exact_ties_go_to_the_lowest_index_on_the_gpu(gp, oracle, variant, mode):
+    """Two or more nodes with the SAME seed hash every object alike: u ties exactly, and with equal weights so does the 64-bit
+    score.  The spec sends the object to the lowest node index.  within_group: the twins sit inside one 32-node group of a
+    class; across_groups: in different groups of one class; across_classes: the table is built with one class per node
+    (dev option), so equal scores meet on the kernels' between-class path (`equal_score_takes` in k_assign_hrw_v2);
+    across_classes_chunked: the same with a table larger than one shared-memory chunk (winner re-hashed from global)."""
+    from rio_rs_b200 import _native as N
+
+    M = {"within_group": 96, "across_groups": 200, "across_classes": 150, "across_classes_chunked": 9000}[mode]
+    os.environ["RIO_ASSIGN_VARIANT"] = variant
+    try:
+        p = provider(gp)
+        addrs, seeds, w = oracle.synth_nodes(M, uniform=True)
+        seeds = seeds.copy()
+        p.set_nodes(addrs, w)
+        if mode == "within_group":
+            twins = [(3, 4), (10, 17), (40, 41), (70, 95)]
+        elif mode == "across_groups":
+            twins = [(3, 44), (10, 170), (64, 199), (31, 32)]
+        else:
+            twins = [(3, 44), (10, 11), (100, 149), (0, M - 1)]
+        for a, b in twins:
+            seeds[b] = seeds[a]
+            p.dev_set_node_seed(b, int(seeds[a]))
+        # a triple, and a tie whose lowest index is NOT the first one met in the class-sorted table order
+        seeds[7] = seeds[5] = seeds[6]
+        p.dev_set_node_seed(5, int(seeds[6]))
+        p.dev_set_node_seed(7, int(seeds[6]))
+        if mode.startswith("across_classes"):
+            p.dev_set_table_options(N.DEV_SPLIT_CLASSES)
+        keys = oracle.synth_keys(300_000 if M < 1000 else 60_000, 7)
+        got = p.assign_batch(keys)
+        want = oracle.assign_hrw(keys, seeds, w, threads=8)
+        assert (got == want).all()
+        # the ties really happened: the upper twin never wins although it scores exactly like the lower one
+        for a, b in twins:
+            assert (want != b).all() and (want == a).sum() > (1.2 * len(keys) / M if M < 1000 else 0)
+        assert (want != 6).all() and (want != 7).all()
+    finally:
+        os.environ.pop("RIO_ASSIGN_VARIANT", None)

@@ -110,3 +110,25 @@ def test_get_or_create_placement_policy(oracle):
     # malformed record is dropped and re-placed (service.rs:213-222)
     m.update("MockService", "3", "garbage")
     assert m.get_or_create_placement("0.0.0.0:5001", "MockService", "3") == "0.0.0.0:5001"
+
+
+def test_check_address_mismatch_restated(oracle):
+    """service.rs:261-298: local -> Ok; active elsewhere -> Redirect; not active -> clean_server + DeallocateServiceObject;
+    no ':' -> Unknown("Malformed address: Missing PORT").  `split(':')` takes the first two pieces only."""
+    m = oracle.DirectoryModel()
+    m.member_push("0.0.0.0", "5000", True)
+    m.member_push("0.0.0.0", "5001", True)
+    m.member_push("0.0.0.0", "5002", False)
+    for i, a in enumerate(["0.0.0.0:5000", "0.0.0.0:5001", "0.0.0.0:5002", "0.0.0.0:5002", "9.9.9.9:1"]):
+        m.update("T", str(i), a)
+    me = "0.0.0.0:5000"
+    assert m.check_address_mismatch(me, me) == oracle.ADDR_LOCAL
+    assert m.check_address_mismatch(me, "0.0.0.0:5001") == oracle.ADDR_REDIRECT
+    assert m.lookup("T", "2") == "0.0.0.0:5002"
+    assert m.check_address_mismatch(me, "0.0.0.0:5002") == oracle.ADDR_DEALLOCATE      # inactive member
+    assert m.lookup("T", "2") is None and m.lookup("T", "3") is None                  # clean_server dropped both
+    assert m.check_address_mismatch(me, "9.9.9.9:1") == oracle.ADDR_DEALLOCATE         # unknown member == not active
+    assert m.lookup("T", "4") is None and m.lookup("T", "1") == "0.0.0.0:5001"
+    assert m.check_address_mismatch(me, "garbage") == oracle.ADDR_MALFORMED
+    assert m.check_address_mismatch(me, "0.0.0.0:5001:extra") == oracle.ADDR_REDIRECT  # ip "0.0.0.0", port "5001": third piece ignored
+    assert m.check_address_mismatch("garbage", "garbage") == oracle.ADDR_LOCAL         # equality is checked before the format
