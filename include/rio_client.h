@@ -41,6 +41,13 @@ uint32_t rio_client_ring_size(const rio_client_ring *ring);
 /* copies at most cap bytes, *out_len = full length */
 int32_t rio_client_ring_address(const rio_client_ring *ring, uint32_t index, char *buf, size_t cap, size_t *out_len);
 
+/* Which of the servers' solver policies the first hop mirrors (include/rio_cuda.h RIO_SOLVER_*): the flat weighted rendezvous
+ * (default) or HRW2, the hierarchical one (trie_bits must equal the servers', 0 = 12).  Under HRW2 the pick
+ * does not depend on the order of `addresses` at all (positions and chains are ordered by a hash of the address). */
+#define RIO_CLIENT_POLICY_HRW  1u
+#define RIO_CLIENT_POLICY_HRW2 2u
+int32_t rio_client_ring_set_policy(rio_client_ring *ring, uint32_t policy, uint32_t trie_bits);
+
 /* == rio_cuda_object_key: hash of the bytes of format!("{}.{}", type, id)  (object_placement/local.rs:26-29) */
 uint64_t rio_client_object_key(const char *type, size_t type_len, const char *id, size_t id_len);
 

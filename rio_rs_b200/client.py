@@ -29,6 +29,7 @@ u32p, u64p, szp = C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_si
 SIGNATURES = {
     "rio_client_ring_create": (C.c_int32, [C.POINTER(C.c_char_p), szp, u32p, C.c_uint32, C.POINTER(C.c_void_p)]),
     "rio_client_ring_destroy": (None, [C.c_void_p]),
+    "rio_client_ring_set_policy": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "rio_client_ring_size": (C.c_uint32, [C.c_void_p]),
     "rio_client_ring_address": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_char_p, C.c_size_t, szp]),
     "rio_client_object_key": (C.c_uint64, [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]),
@@ -70,7 +71,8 @@ def object_key(type_name, object_id):
 class FirstHop:
     """The client's placement cache + first-hop pick.  `cache_size` = the reference's LruCache limit (client/mod.rs:137)."""
 
-    def __init__(self, addresses=(), weights=None, cache_size=1000):
+    def __init__(self, addresses=(), weights=None, cache_size=1000, policy="hrw", trie_bits=0):
+        self._policy, self._bits = (2 if policy == "hrw2" else 1), trie_bits
         self._ring = C.c_void_p()
         self._cache = collections.OrderedDict()
         self._cache_size = cache_size
@@ -104,6 +106,8 @@ class FirstHop:
         st = lib().rio_client_ring_create(arr, lens, w.ctypes.data_as(u32p) if w is not None else None, n, C.byref(ring))
         if st != 0:
             raise ValueError("rio_client_ring_create failed")
+        if lib().rio_client_ring_set_policy(ring, self._policy, self._bits) != 0:
+            raise ValueError("rio_client_ring_set_policy failed")
         self.close()
         self._ring, self.addresses = ring, addresses
 

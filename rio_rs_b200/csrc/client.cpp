@@ -2,6 +2,7 @@
 // Plain C++ (g++), no CUDA: a client resolves one id at a time on its own CPU.  Shares spec.cuh with the kernels.
 #include "../../include/rio_client.h"
 
+#include <algorithm>
 #include <new>
 #include <string>
 #include <vector>
@@ -14,6 +15,15 @@ struct rio_client_ring {
     std::vector<std::string> addr;
     struct Node { uint32_t s0, m, s2, invw; };   // invw == 0: not live
     std::vector<Node> nodes;
+    std::vector<uint64_t> seed;
+    std::vector<uint32_t> weight;
+    // HRW2: thresholds of the binary trie over node positions in heap order, one leaf word per bucket, and the
+    // member-keyed chain records of buckets that hold more than one node -- the same table the servers' kernels walk
+    uint32_t policy = RIO_CLIENT_POLICY_HRW, bits = 12;
+    std::vector<uint32_t> tab32;                       // [0, 2^bits) thresholds T3, [2^bits, 2^(bits+1)) leaf words
+    struct Chain { uint32_t s0, m2, h2, t3, idx; };
+    std::vector<Chain> chain;
+    std::vector<ContestRec> level;
 };
 
 namespace {
@@ -32,9 +42,63 @@ uint32_t first_hop(const rio_client_ring &r, uint64_t key) {
     return best;
 }
 
+void build_trie(rio_client_ring &r) {
+    const uint32_t bits = r.bits, nb = 1u << bits;
+    struct Mem { uint64_t pos; uint32_t idx, w; };
+    std::vector<Mem> mem;
+    for (uint32_t j = 0; j < (uint32_t)r.seed.size(); j++) if (r.weight[j]) mem.push_back(Mem{mix64(r.seed[j] ^ kSaltPos), j, r.weight[j]});
+    std::sort(mem.begin(), mem.end(), [](const Mem &a, const Mem &b) { return a.pos != b.pos ? a.pos < b.pos : a.idx < b.idx; });
+    std::vector<uint64_t> wsum((size_t)2 * nb, 0);
+    std::vector<uint32_t> bstart((size_t)nb + 1, 0);
+    for (const Mem &m : mem) { const uint32_t bk = bits ? (uint32_t)(m.pos >> (64 - bits)) : 0u; wsum[nb + bk] += m.w; bstart[bk + 1]++; }
+    for (uint32_t k = 0; k < nb; k++) bstart[k + 1] += bstart[k];
+    for (uint32_t i = nb - 1; i >= 1; i--) wsum[i] = wsum[2 * i] + wsum[2 * i + 1];
+    r.tab32.assign((size_t)2 * nb, 0);
+    for (uint32_t i = 1; i < nb; i++) r.tab32[i] = contest_t3(wsum[2 * i], wsum[2 * i + 1]);
+    r.chain.clear();
+    for (uint32_t k = 0; k < nb; k++) {
+        const uint32_t lo = bstart[k], hi = bstart[k + 1];
+        if (lo == hi) { r.tab32[nb + k] = kNone; continue; }
+        if (hi - lo == 1) { r.tab32[nb + k] = mem[lo].idx; continue; }
+        r.tab32[nb + k] = 0x80000000u | (uint32_t)r.chain.size();
+        uint64_t rest = wsum[nb + k];
+        for (uint32_t q = lo; q < hi; q++) {
+            rest -= mem[q].w;
+            const ContestRec c = contest_rec(r.seed[mem[q].idx]);
+            r.chain.push_back({c.s0, c.m2, c.h2, q + 1 == hi ? 0xFFFFFFFFu : contest_t3(mem[q].w, rest), mem[q].idx});
+        }
+    }
+    r.level.clear();
+    for (uint32_t l = 0; l < bits; l++) r.level.push_back(contest_rec(level_seed(l)));
+}
+
+uint32_t first_hop_hrw2(const rio_client_ring &r, uint64_t key) {
+    const ObjHash o = obj_hash(key);
+    uint32_t i = 1;
+    for (uint32_t l = 0; l < r.bits; l++) i = 2 * i + (contest_u(o, r.level[l].s0, r.level[l].m2, r.level[l].h2) > r.tab32[i] ? 1u : 0u);
+    const uint32_t leaf = r.tab32[i];
+    if (leaf == kNone || !(leaf & 0x80000000u)) return leaf;
+    for (uint32_t pos = leaf & 0x7FFFFFFFu;; pos++) {
+        const rio_client_ring::Chain &c = r.chain[pos];
+        if (contest_u(o, c.s0, c.m2, c.h2) <= c.t3) return c.idx;
+    }
+}
+
+uint32_t pick(const rio_client_ring &r, uint64_t key) { return r.policy == RIO_CLIENT_POLICY_HRW2 ? first_hop_hrw2(r, key) : first_hop(r, key); }
+
 }  // namespace
 
 extern "C" {
+
+int32_t rio_client_ring_set_policy(rio_client_ring *ring, uint32_t policy, uint32_t trie_bits) {
+    if (!ring || (policy != RIO_CLIENT_POLICY_HRW && policy != RIO_CLIENT_POLICY_HRW2) || trie_bits > 14) return RIO_CLIENT_ERR;
+    try {
+        ring->policy = policy;
+        if (trie_bits) ring->bits = trie_bits;
+        if (policy == RIO_CLIENT_POLICY_HRW2) build_trie(*ring);
+    } catch (...) { return RIO_CLIENT_ERR; }
+    return RIO_CLIENT_OK;
+}
 
 int32_t rio_client_ring_create(const char *const *addresses, const size_t *address_lens, const uint32_t *weights, uint32_t n, rio_client_ring **out) {
     if (!out || (n && (!addresses || !address_lens))) return RIO_CLIENT_ERR;
@@ -47,6 +111,8 @@ int32_t rio_client_ring_create(const char *const *addresses, const size_t *addre
             const uint64_t seed = mix64(fnv1a64(addresses[j], address_lens[j]));
             const uint64_t seed2 = mix64(seed ^ kSaltNode2);
             r->nodes.push_back({(uint32_t)seed, (uint32_t)(seed >> 32) | 1u, (uint32_t)seed2, inv_weight(weights ? weights[j] : 1u)});
+            r->seed.push_back(seed);
+            r->weight.push_back(weights ? weights[j] : 1u);
         }
     } catch (...) { delete r; return RIO_CLIENT_ERR; }
     *out = r;
@@ -75,19 +141,19 @@ uint64_t rio_client_object_key(const char *type, size_t type_len, const char *id
 
 int32_t rio_client_first_hop_key(const rio_client_ring *ring, uint64_t key, uint32_t *out_index) {
     if (!ring || !out_index) return RIO_CLIENT_ERR;
-    *out_index = first_hop(*ring, key);
+    *out_index = pick(*ring, key);
     return RIO_CLIENT_OK;
 }
 
 int32_t rio_client_first_hop(const rio_client_ring *ring, const char *type, size_t type_len, const char *id, size_t id_len, uint32_t *out_index) {
     if (!ring || !out_index || (!type && type_len) || (!id && id_len)) return RIO_CLIENT_ERR;
-    *out_index = first_hop(*ring, rio_client_object_key(type, type_len, id, id_len));
+    *out_index = pick(*ring, rio_client_object_key(type, type_len, id, id_len));
     return RIO_CLIENT_OK;
 }
 
 int32_t rio_client_first_hop_batch(const rio_client_ring *ring, const uint64_t *keys, size_t n, uint32_t *out_index) {
     if (!ring || (n && (!keys || !out_index))) return RIO_CLIENT_ERR;
-    for (size_t i = 0; i < n; i++) out_index[i] = first_hop(*ring, keys[i]);
+    for (size_t i = 0; i < n; i++) out_index[i] = pick(*ring, keys[i]);
     return RIO_CLIENT_OK;
 }
 

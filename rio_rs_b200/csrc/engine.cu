@@ -109,10 +109,18 @@ struct NodeInfo {
     bool live() const { return active && weight > 0 && !malformed; }
 };
 
+// Every array a table build produces is laid out in ONE pinned staging area and crosses PCIe as ONE copy; the device side is a
+// single allocation the kernels' pointers index into.  A membership event therefore costs one host-side build (~0.1 ms at 1024
+// nodes), one H2D of ~70 KB and no synchronisation of its own.
 struct TabBufs {
-    DevBuf recs, classes, by_idx, trie_blob;
+    DevBuf dev;
+    unsigned char *stage = nullptr;   // pinned
+    size_t stage_cap = 0;
+    bool upload_pending = false;
     NodeTabDev tab{};
     TrieDev trie{};
+    const uint8_t *state = nullptr;   // per interned node: kNodeLive | kNodeMalformed (the policy's view)
+    const uint32_t *live = nullptr;   // per interned node: solver eligibility (active, weight > 0)
 };
 
 // device scalars (one small allocation): [0]=nsel [1]=moved/removed [2]=new keys (cumulative) [3]=placed ; u32 error at [8]
@@ -136,7 +144,7 @@ struct rio_placement {
     uint32_t trie_bits = 12;            // HRW2: depth of the binary trie over node positions
     bool tab_dirty = true;
     TabBufs tabs, tabs_masked;
-    DevBuf d_node_state, d_live, d_fnode, d_fnode_c, d_fnode_g, d_nidx_map;
+    DevBuf d_fnode, d_fnode_c, d_fnode_g, d_nidx_map;
     uint32_t aff_live = 0, aff_pad = 0;   // compacted live-node operands of the tcgen05 affinity kernel
 
     DirDev dir{};
@@ -146,8 +154,9 @@ struct rio_placement {
     uint32_t dir_seq = 0;           // upsert sequence numbers handed out so far (ordering of duplicate keys, k_dir_upsert)
 
     DevBuf s_keys, s_idx, s_idx2, s_sel, s_slots, s_keys2, s_feats, s_packed, s_offsets, s_cost, s_misc, s_flush, s_gather;
-    // bounded-load state kept on the device between passes: [cap u32 | global counters u32 | thr u32 | over u8 | closed u8] x node
+    // bounded-load state kept on the device between passes: [ticket | cap | global counters | thr | closed epoch | over] x node
     DevBuf d_bounded;
+    uint32_t bounded_epoch = 0;               // closed-set tag of the current bounded call
     uint64_t cap_key[4] = {~0ull, 0, 0, 0};   // (n_total_objs, num << 32 | den, table version, M) the uploaded capacities belong to
     uint64_t tab_version = 0;
     unsigned long long *d_scalars = nullptr;   // S_COUNT u64 + error u32
@@ -171,9 +180,10 @@ struct rio_placement {
 struct rio_objset {
     rio_placement *h = nullptr;
     uint64_t capacity = 0, n = 0;
-    DevBuf keys, idx, feats, counters, sel;
+    DevBuf keys, idx, feats, counters, counters_alt, sel;
     uint32_t K = 0;
     uint32_t counters_n = 0;
+    bool alt_zero = false;     // counters_alt is known to be all zero (the capacity check of the last bounded pass cleared it)
     bool assigned = false;
 };
 
@@ -275,51 +285,67 @@ void build_tab(rio_placement *h, TabBufs &tb, const std::vector<uint8_t> *closed
     }
     const uint32_t off_crec = (uint32_t)((tab32.size() * 4 + 15) / 16 * 16);
     const uint32_t off_cnidx = off_crec + (uint32_t)crec.size() * 16;
-    const uint32_t blob_bytes = (uint32_t)((off_cnidx + cnidx.size() * 4 + 15) / 16 * 16);
-    std::vector<unsigned char> blob(blob_bytes ? blob_bytes : 16, 0);
-    memcpy(blob.data(), tab32.data(), tab32.size() * 4);
-    if (!crec.empty()) { memcpy(blob.data() + off_crec, crec.data(), crec.size() * 16); memcpy(blob.data() + off_cnidx, cnidx.data(), cnidx.size() * 4); }
+    const uint32_t blob_bytes = std::max<uint32_t>(16u, (uint32_t)((off_cnidx + cnidx.size() * 4 + 15) / 16 * 16));
+    // the policy's view of every interned node (service.rs:226-231 asks is_active only: a draining node -- active, weight 0 --
+    // keeps its objects) and the solver's (active and weight > 0)
+    std::vector<uint8_t> state(n_total ? n_total : 1, 0);
+    std::vector<uint32_t> livef(n_total ? n_total : 1, 0);
+    for (uint32_t j = 0; j < n_total; j++) {
+        const NodeInfo &ni = h->nodes[j];
+        state[j] = ((ni.active && !ni.malformed) ? kNodeLive : 0) | (ni.malformed ? kNodeMalformed : 0);
+        livef[j] = ni.live() ? 1u : 0u;
+    }
 
+    // ---- one staging area, one copy ----
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t o_recs = 0, o_classes = al(o_recs + recs.size() * sizeof(NodeRec)), o_byidx = al(o_classes + classes.size() * sizeof(ClassRec)),
+                 o_trie = al(o_byidx + by_idx.size() * sizeof(uint4)), o_state = al(o_trie + blob_bytes), o_live = al(o_state + state.size()),
+                 total = al(o_live + livef.size() * 4);
     cudaStream_t st = h->stream;
-    tb.trie_blob.ensure(blob.size(), st);
-    CUDA_TRY(cudaMemcpyAsync(tb.trie_blob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, st));
-    tb.trie = TrieDev{tb.trie_blob.p, (uint32_t)blob.size(), off_crec, off_cnidx, bits, (uint32_t)crec.size()};
-    tb.recs.ensure(recs.size() * sizeof(NodeRec), st);
-    tb.classes.ensure(classes.size() * sizeof(ClassRec), st);
-    tb.by_idx.ensure(by_idx.size() * sizeof(uint4), st);
-    CUDA_TRY(cudaMemcpyAsync(tb.recs.p, recs.data(), recs.size() * sizeof(NodeRec), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(tb.classes.p, classes.data(), classes.size() * sizeof(ClassRec), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(tb.by_idx.p, by_idx.data(), by_idx.size() * sizeof(uint4), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaStreamSynchronize(st));   // host vectors go out of scope
-    tb.tab.recs = tb.recs.as<NodeRec>();
-    tb.tab.classes = tb.classes.as<ClassRec>();
-    tb.tab.by_idx = tb.by_idx.as<uint4>();
+    if (tb.upload_pending) { CUDA_TRY(cudaStreamSynchronize(st)); tb.upload_pending = false; }   // the previous copy still reads the staging area
+    if (total > tb.stage_cap) {
+        if (tb.stage) CUDA_TRY(cudaFreeHost(tb.stage));
+        tb.stage = nullptr; tb.stage_cap = 0;
+        CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&tb.stage), total * 2));
+        tb.stage_cap = total * 2;
+    }
+    memset(tb.stage + o_trie, 0, blob_bytes);
+    memcpy(tb.stage + o_recs, recs.data(), recs.size() * sizeof(NodeRec));
+    memcpy(tb.stage + o_classes, classes.data(), classes.size() * sizeof(ClassRec));
+    memcpy(tb.stage + o_byidx, by_idx.data(), by_idx.size() * sizeof(uint4));
+    memcpy(tb.stage + o_trie, tab32.data(), tab32.size() * 4);
+    if (!crec.empty()) { memcpy(tb.stage + o_trie + off_crec, crec.data(), crec.size() * 16); memcpy(tb.stage + o_trie + off_cnidx, cnidx.data(), cnidx.size() * 4); }
+    memcpy(tb.stage + o_state, state.data(), state.size());
+    memcpy(tb.stage + o_live, livef.data(), livef.size() * 4);
+    tb.dev.ensure(total, st);
+    CUDA_TRY(cudaMemcpyAsync(tb.dev.p, tb.stage, total, cudaMemcpyHostToDevice, st));
+    tb.upload_pending = true;
+    unsigned char *d = tb.dev.as<unsigned char>();
+    tb.trie = TrieDev{d + o_trie, blob_bytes, off_crec, off_cnidx, bits, (uint32_t)crec.size()};
+    tb.tab.recs = reinterpret_cast<const NodeRec *>(d + o_recs);
+    tb.tab.classes = reinterpret_cast<const ClassRec *>(d + o_classes);
+    tb.tab.by_idx = reinterpret_cast<const uint4 *>(d + o_byidx);
     tb.tab.n_live = (uint32_t)live.size();
     tb.tab.n_classes = n_classes;
     tb.tab.n_total = n_total;
+    tb.state = d + o_state;
+    tb.live = reinterpret_cast<const uint32_t *>(d + o_live);
 }
 
 void ensure_tab(rio_placement *h) {
     if (!h->tab_dirty) return;
     build_tab(h, h->tabs, nullptr);
     const uint32_t n_total = (uint32_t)h->nodes.size();
-    std::vector<uint8_t> state(n_total ? n_total : 1, 0);
-    std::vector<uint32_t> live(n_total ? n_total : 1, 0);
-    std::vector<float> fnode((size_t)(n_total ? n_total : 1) * (h->K ? h->K : 1), 0.f);
+    cudaStream_t st = h->stream;
+    h->tab_dirty = false;
+    h->tab_version++;
+    if (!h->K) return;   // hash path only: nothing else to upload, and no synchronisation
+    std::vector<float> fnode((size_t)(n_total ? n_total : 1) * h->K, 0.f);
     for (uint32_t j = 0; j < n_total; j++) {
         const NodeInfo &ni = h->nodes[j];
-        // the per-request policy asks is_active(ip, port) only (storage/mod.rs:102-110): a draining node (active, weight 0) keeps its
-        // objects; weight > 0 matters to the solver alone (live[], the class table, the trie)
-        state[j] = ((ni.active && !ni.malformed) ? kNodeLive : 0) | (ni.malformed ? kNodeMalformed : 0);
-        live[j] = ni.live() ? 1u : 0u;
-        if (h->K && ni.feat.size() == h->K) std::copy(ni.feat.begin(), ni.feat.end(), fnode.begin() + (size_t)j * h->K);   // others keep zeros
+        if (ni.feat.size() == h->K) std::copy(ni.feat.begin(), ni.feat.end(), fnode.begin() + (size_t)j * h->K);   // others keep zeros
     }
-    cudaStream_t st = h->stream;
-    h->d_node_state.ensure(state.size(), st);
-    h->d_live.ensure(live.size() * 4, st);
     h->d_fnode.ensure(fnode.size() * 4, st);
-    CUDA_TRY(cudaMemcpyAsync(h->d_node_state.p, state.data(), state.size(), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(h->d_live.p, live.data(), live.size() * 4, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(h->d_fnode.p, fnode.data(), fnode.size() * 4, cudaMemcpyHostToDevice, st));
     // compacted live nodes (node-index order) for the tensor-core affinity kernel, zero padded to the node tile
     h->aff_live = h->aff_pad = 0;
@@ -346,9 +372,7 @@ void ensure_tab(rio_placement *h) {
         CUDA_TRY(cudaStreamSynchronize(st));
         h->aff_live = nl; h->aff_pad = pad;
     }
-    CUDA_TRY(cudaStreamSynchronize(st));
-    h->tab_dirty = false;
-    h->tab_version++;
+    CUDA_TRY(cudaStreamSynchronize(st));   // the host vectors above go out of scope
 }
 
 // ---- directory sizing ---------------------------------------------------------------------------------------
@@ -438,7 +462,7 @@ void run_affinity(rio_placement *h, const float *d_fobj, uint64_t n, uint32_t *d
                                         d_counters))
             return;
     }
-    launch_assign_affinity(h->L(), d_fobj, n, h->d_fnode.as<float>(), h->d_live.as<uint32_t>(), h->tabs.tab.n_total, h->K, d_out_idx, d_out_cost, d_counters);
+    launch_assign_affinity(h->L(), d_fobj, n, h->d_fnode.as<float>(), h->tabs.live, h->tabs.tab.n_total, h->K, d_out_idx, d_out_cost, d_counters);
 }
 
 uint32_t capacity_of(uint64_t n_total, uint32_t w, uint64_t w_sum, uint32_t num, uint32_t den) {
@@ -484,48 +508,73 @@ void assign_host_pipelined(rio_placement *h, const uint64_t *keys, const float *
 }
 
 // ---- bounded-load rounds over a device-resident (keys, idx, counters) triple ------------------------------------
-// Pass 0 = plain assignment with the fused histogram.  After every pass ONE small kernel does the counter exchange (peer
-// memory, world > 1) and the capacity check on the device and leaves two words in mapped pinned memory; the host reads those
-// after the stream synchronises.  Only when a node is over capacity (rare at the default factor 1.25) do the thresholds get
-// used by the spill selection and the closed set come back to the host for the masked table of the next pass.
-struct BoundedDev { uint32_t *cap, *glob, *thr; uint8_t *over, *closed; };
+// Pass 0 = plain assignment with the fused histogram.  The counter exchange (peer memory, world > 1) and the capacity check run on
+// the device -- under HRW2 in the last CTA of the walk kernel itself, otherwise as one small kernel behind it -- and leave two
+// words in mapped pinned memory; the host reads those after the stream synchronises.  Only when a node is over capacity (rare at
+// the default factor 1.25) do the thresholds get used by the spill selection and the closed set come back to the host for the
+// masked table of the next pass.
+struct BoundedDev { uint32_t *cap, *glob, *thr, *closed_epoch, *ticket; uint8_t *over; };
 BoundedDev bounded_layout(rio_placement *h, uint32_t M) {
     const size_t m = std::max(M, 1u);
-    h->d_bounded.ensure(m * 14 + 64, h->stream);
+    const size_t need = m * 17 + 64;
+    if (need > h->d_bounded.bytes) {
+        h->d_bounded.ensure(need, h->stream);
+        CUDA_TRY(cudaMemsetAsync(h->d_bounded.p, 0, h->d_bounded.bytes, h->stream));   // closed epochs and the ticket start at 0
+        h->bounded_epoch = 0;
+        h->cap_key[0] = ~0ull;
+    }
     BoundedDev b;
-    b.cap = h->d_bounded.as<uint32_t>();
+    b.ticket = h->d_bounded.as<uint32_t>();          // 16 words reserved
+    b.cap = b.ticket + 16;
     b.glob = b.cap + m;
     b.thr = b.glob + m;
-    b.over = reinterpret_cast<uint8_t *>(b.thr + m);
-    b.closed = b.over + m;
+    b.closed_epoch = b.thr + m;
+    b.over = reinterpret_cast<uint8_t *>(b.closed_epoch + m);
     return b;
 }
 
-// one exchange + check; returns {any over, open nodes}
-std::pair<uint32_t, uint32_t> exchange_and_check(rio_placement *h, const uint32_t *d_local, const BoundedDev &b, uint32_t M) {
-    volatile uint32_t *flags = reinterpret_cast<volatile uint32_t *>(h->h_scalars + S_FLAGS);
-    uint32_t *flags_dev = nullptr;
-    CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void **>(&flags_dev), const_cast<uint32_t *>(flags), 0));
-    const uint8_t *state = h->d_node_state.as<uint8_t>();
-    if (h->world > 1 && h->xchg_ready && M <= h->xchg_nodes) {
-        launch_exchange_check(h->L(), d_local, h->xchg_peer, (uint32_t)h->rank, (uint32_t)h->world, M, h->xchg_nodes, ++h->xchg_epoch, b.glob, b.cap, state,
-                              b.closed, b.thr, b.over, flags_dev);
-    } else {
-        const uint32_t *src = d_local;
-        if (h->world > 1 && h->comm) {   // portable path: NCCL all-gather + sum, then the check alone
-            h->s_gather.ensure((size_t)M * 4 * h->world, h->stream);
-            NCCL_TRY(g_nccl.AllGather(d_local, h->s_gather.p, M, kNcclUint32, h->comm, h->stream));
-            launch_sum_gathered(h->L(), h->s_gather.as<uint32_t>(), (uint32_t)h->world, M, b.glob);
-            src = b.glob;
-        }
-        launch_exchange_check(h->L(), src, nullptr, 0, 1, M, 0, 0, b.glob, b.cap, state, b.closed, b.thr, b.over, flags_dev);
+BoundedTail make_tail(rio_placement *h, const BoundedDev &b, uint32_t M, uint32_t *next_zero, bool peer_exchange) {
+    BoundedTail t{};
+    t.enabled = 1;
+    t.M = M;
+    t.ticket = b.ticket;
+    t.next_zero = next_zero;
+    t.world = 1;
+    if (peer_exchange) {
+        for (int p = 0; p < h->world && p < 16; p++) t.peers.win[p] = h->xchg_peer[p];
+        t.rank = (uint32_t)h->rank; t.world = (uint32_t)h->world; t.max_nodes = h->xchg_nodes; t.xchg_epoch = ++h->xchg_epoch;
     }
+    t.glob = b.glob; t.cap = b.cap; t.state = h->tabs.state; t.closed_epoch = b.closed_epoch; t.call_epoch = h->bounded_epoch;
+    t.thr = b.thr; t.over = b.over;
+    uint32_t *flags_dev = nullptr;
+    CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void **>(&flags_dev), h->h_scalars + S_FLAGS, 0));
+    t.host_flags = flags_dev;
+    return t;
+}
+
+std::pair<uint32_t, uint32_t> read_flags(rio_placement *h) {
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    const volatile uint32_t *flags = reinterpret_cast<const volatile uint32_t *>(h->h_scalars + S_FLAGS);
     return {flags[0], flags[1]};
 }
 
+// one exchange + check as its own launch; returns {any over, open nodes}
+std::pair<uint32_t, uint32_t> exchange_and_check(rio_placement *h, const uint32_t *d_local, const BoundedDev &b, uint32_t M, uint32_t *next_zero) {
+    const bool p2p = h->world > 1 && h->xchg_ready && M <= h->xchg_nodes;
+    const uint32_t *src = d_local;
+    if (!p2p && h->world > 1 && h->comm) {   // portable path: NCCL all-gather + sum, then the check alone
+        h->s_gather.ensure((size_t)M * 4 * h->world, h->stream);
+        NCCL_TRY(g_nccl.AllGather(d_local, h->s_gather.p, M, kNcclUint32, h->comm, h->stream));
+        launch_sum_gathered(h->L(), h->s_gather.as<uint32_t>(), (uint32_t)h->world, M, b.glob);
+        src = b.glob;
+    }
+    launch_exchange_check(h->L(), src, make_tail(h, b, M, next_zero, p2p));
+    return read_flags(h);
+}
+
 uint32_t bounded_rounds(rio_placement *h, const uint64_t *d_keys, uint64_t n, uint32_t *d_idx, uint32_t *d_counters, uint32_t *d_sel, uint32_t M,
-                        uint64_t n_total_objs, uint32_t cap_num, uint32_t cap_den, uint32_t max_rounds, bool first_pass_done) {
+                        uint64_t n_total_objs, uint32_t cap_num, uint32_t cap_den, uint32_t max_rounds, bool first_pass_done, bool counters_zeroed,
+                        uint32_t *next_zero) {
     cudaStream_t st = h->stream;
     const BoundedDev b = bounded_layout(h, M);
     const uint64_t key[4] = {n_total_objs, ((uint64_t)cap_num << 32) | cap_den, h->tab_version, M};
@@ -538,20 +587,34 @@ uint32_t bounded_rounds(rio_placement *h, const uint64_t *d_keys, uint64_t n, ui
         CUDA_TRY(cudaStreamSynchronize(st));
         memcpy(h->cap_key, key, sizeof key);
     }
-    CUDA_TRY(cudaMemsetAsync(b.closed, 0, std::max(M, 1u), st));
+    if (++h->bounded_epoch == 0) {   // the closed set of a call is "closed_epoch[j] == this call's epoch": no memset per call
+        CUDA_TRY(cudaMemsetAsync(b.closed_epoch, 0, (size_t)std::max(M, 1u) * 4, st));
+        h->bounded_epoch = 1;
+    }
+    bool fused = false;
     if (!first_pass_done) {
-        CUDA_TRY(cudaMemsetAsync(d_counters, 0, (size_t)std::max(M, 1u) * 4, st));
-        run_assign(h, h->solver, h->tabs, d_keys, n, d_idx, d_counters, nullptr, 0);
+        if (!counters_zeroed) CUDA_TRY(cudaMemsetAsync(d_counters, 0, (size_t)std::max(M, 1u) * 4, st));
+        const bool p2p = h->world > 1 && h->xchg_ready && M <= h->xchg_nodes;
+        if (max_rounds > 1 && h->solver == RIO_SOLVER_HRW2 && (h->world == 1 || p2p)) {
+            const BoundedTail t = make_tail(h, b, M, next_zero, p2p);   // walk + histogram + exchange + check: ONE launch
+            launch_assign_trie(h->L(), d_keys, n, h->tabs.trie, d_idx, d_counters, nullptr, 0, h->tabs.tab.n_total, &t);
+            fused = true;
+        } else {
+            run_assign(h, h->solver, h->tabs, d_keys, n, d_idx, d_counters, nullptr, 0);
+        }
     }
     uint32_t passes = 1;
     for (uint32_t r = 1; r < max_rounds; r++) {
-        const auto [any, open] = exchange_and_check(h, d_counters, b, M);                  // the one collective of this pass
+        const auto [any, open] = fused ? read_flags(h) : exchange_and_check(h, d_counters, b, M, next_zero);   // the one collective of this pass
+        fused = false;
         if (!any || !open) break;
         zero_scalar(h, S_NSEL);
         launch_select_spill(h->L(), d_keys, d_idx, n, b.thr, b.over, r, d_sel, h->d_scalars + S_NSEL, d_counters);
-        std::vector<uint8_t> closed(M, 0);
-        CUDA_TRY(cudaMemcpyAsync(closed.data(), b.closed, M, cudaMemcpyDeviceToHost, st));
+        std::vector<uint32_t> ce(M, 0);
+        CUDA_TRY(cudaMemcpyAsync(ce.data(), b.closed_epoch, (size_t)M * 4, cudaMemcpyDeviceToHost, st));
         const uint64_t nsel = read_scalar(h, S_NSEL);
+        std::vector<uint8_t> closed(M, 0);
+        for (uint32_t j = 0; j < M; j++) closed[j] = ce[j] == h->bounded_epoch;
         build_tab(h, h->tabs_masked, &closed);
         if (nsel) run_assign(h, h->solver, h->tabs_masked, d_keys, n, d_idx, d_counters, d_sel, nsel);
         passes++;
@@ -597,6 +660,9 @@ void set_ensure_counters(rio_objset *s) {
         s->counters.release(h->stream);
         s->counters = nb;
         s->counters_n = n_total;
+        s->counters_alt.release(h->stream);
+        s->counters_alt.ensure(nb.bytes, h->stream);
+        s->alt_zero = false;
     }
 }
 
@@ -675,8 +741,8 @@ void rio_cuda_destroy(rio_placement *h) {
             if (h->xchg_ready && p != h->rank && h->xchg_peer[p]) cudaIpcCloseMemHandle(h->xchg_peer[p]);
         cudaFree(h->xchg_mine);
     }
-    DevBuf *bufs[] = {&h->tabs.recs, &h->tabs.classes, &h->tabs.by_idx, &h->tabs_masked.recs, &h->tabs_masked.classes, &h->tabs_masked.by_idx, &h->tabs.trie_blob, &h->tabs_masked.trie_blob,
-                      &h->d_node_state, &h->d_live, &h->d_fnode, &h->d_fnode_c, &h->d_fnode_g, &h->d_nidx_map, &h->s_keys, &h->s_idx, &h->s_idx2, &h->s_sel, &h->s_slots, &h->s_keys2, &h->s_feats,
+    for (TabBufs *tb : {&h->tabs, &h->tabs_masked}) if (tb->stage) cudaFreeHost(tb->stage);
+    DevBuf *bufs[] = {&h->tabs.dev, &h->tabs_masked.dev, &h->d_fnode, &h->d_fnode_c, &h->d_fnode_g, &h->d_nidx_map, &h->s_keys, &h->s_idx, &h->s_idx2, &h->s_sel, &h->s_slots, &h->s_keys2, &h->s_feats,
                       &h->s_packed, &h->s_offsets, &h->s_cost, &h->s_misc, &h->s_flush, &h->s_gather, &h->d_bounded};
     for (DevBuf *b : bufs) b->release(h->stream);
     if (h->dir.slots) cudaFreeAsync(h->dir.slots, h->stream);
@@ -946,7 +1012,7 @@ rio_status rio_cuda_assign_bounded_batch(rio_placement *h, const uint64_t *keys,
         // indices are still crossing PCIe
         assign_host_pipelined(h, keys, nullptr, n, out_idx, d_cnt, false);
         const uint32_t passes = bounded_rounds(h, h->s_keys.as<uint64_t>(), n, h->s_idx.as<uint32_t>(), d_cnt, h->s_sel.as<uint32_t>(), M, n_total_objs, cap_num, cap_den,
-                                               max_rounds, true);
+                                               max_rounds, true, true, nullptr);
         CUDA_TRY(cudaStreamSynchronize(h->d2h_stream));
         if (passes > 1) {   // a spill round rewrote some indices after their chunk had left: send the final state again
             CUDA_TRY(cudaMemcpyAsync(out_idx, h->s_idx.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -1006,7 +1072,7 @@ rio_status rio_cuda_place_batch(rio_placement *h, const uint64_t *keys, size_t n
         launch_dir_lookup(h->L(), h->dir, h->s_keys.as<uint64_t>(), n, h->s_idx.as<uint32_t>());                          // service.rs:199-201
         zero_scalar(h, S_NSEL);
         CUDA_TRY(cudaMemsetAsync(h->s_misc.p, 0, std::max<size_t>(n_total, 1), st));
-        launch_classify(h->L(), h->s_idx.as<uint32_t>(), n, h->d_node_state.as<uint8_t>(), n_total, h->s_sel.as<uint32_t>(), h->d_scalars + S_NSEL,
+        launch_classify(h->L(), h->s_idx.as<uint32_t>(), n, h->tabs.state, n_total, h->s_sel.as<uint32_t>(), h->d_scalars + S_NSEL,
                         h->s_misc.as<uint8_t>());
         const uint64_t nsel = read_scalar(h, S_NSEL);
         if (nsel) {
@@ -1131,7 +1197,7 @@ void rio_cuda_set_destroy(rio_objset *s) {
     {
         std::lock_guard<std::mutex> g(h->mu);
         cudaSetDevice(h->device);
-        s->keys.release(h->stream); s->idx.release(h->stream); s->feats.release(h->stream); s->counters.release(h->stream); s->sel.release(h->stream);
+        s->keys.release(h->stream); s->idx.release(h->stream); s->feats.release(h->stream); s->counters.release(h->stream); s->counters_alt.release(h->stream); s->sel.release(h->stream);
         cudaStreamSynchronize(h->stream);
     }
     delete s;
@@ -1195,8 +1261,12 @@ rio_status rio_cuda_set_assign_bounded(rio_objset *s, uint64_t n_total_objs, uin
         ensure_tab(h);
         set_ensure_counters(s);
         if (!n_total_objs) n_total_objs = s->n * (uint64_t)h->world;
+        // two counter buffers take turns: the check of this pass clears the other one, so the next pass starts without a memset
+        const bool zeroed = s->alt_zero;
+        if (zeroed) std::swap(s->counters, s->counters_alt);
         const uint32_t passes = bounded_rounds(h, s->keys.as<uint64_t>(), s->n, s->idx.as<uint32_t>(), s->counters.as<uint32_t>(), s->sel.as<uint32_t>(), s->counters_n,
-                                               n_total_objs, cap_num, cap_den, max_rounds, false);
+                                               n_total_objs, cap_num, cap_den, max_rounds, false, zeroed, s->counters_alt.as<uint32_t>());
+        s->alt_zero = max_rounds > 1;
         s->assigned = true;
         if (out_passes) *out_passes = passes;
         CUDA_TRY(cudaStreamSynchronize(h->stream));

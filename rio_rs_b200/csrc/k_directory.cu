@@ -3,6 +3,7 @@
 // two slots), 128-bit loads on the scans, warp-aggregated counters.
 #include "kernels.cuh"
 #include "spec.cuh"
+#include "bounded_tail.cuh"
 
 namespace rio {
 
@@ -219,90 +220,131 @@ __device__ __forceinline__ bool join_wins(uint64_t key, uint32_t cur, uint32_t n
 }
 
 // The incumbent's node record is a random 16-byte gather: from L1 that costs one wavefront per distinct line (up to 32 per
-// warp load), so the by-index table is staged in shared memory when it fits (smem_nodes != 0).
-__device__ __forceinline__ const uint4 *stage_by_idx(const NodeTabDev &tab, uint32_t smem_nodes) {
+// warp load), so the by-index table is staged in shared memory when it fits (template SMEM; LDS.128, not generic LD).
+template <bool SMEM>
+__device__ __forceinline__ const uint4 *stage_by_idx(const NodeTabDev &tab) {
     extern __shared__ __align__(16) unsigned char smem_dir[];
-    if (!smem_nodes) return tab.by_idx;
+    if (!SMEM) return tab.by_idx;
     uint4 *s = reinterpret_cast<uint4 *>(smem_dir);
     for (uint32_t j = threadIdx.x; j < tab.n_total; j += blockDim.x) s[j] = __ldg(tab.by_idx + j);
     __syncthreads();
     return s;
 }
 
-__global__ void __launch_bounds__(256)
-k_rebalance_join(const uint64_t *__restrict__ keys, uint32_t *__restrict__ idx, uint64_t n, NodeTabDev tab, uint32_t new_idx,
-                 uint32_t *__restrict__ counters, unsigned long long *moved, uint32_t smem_nodes) {
-    const uint4 *by_idx = stage_by_idx(tab, smem_nodes);
-    const uint4 nn = __ldg(tab.by_idx + new_idx);
-    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t i = base + threadIdx.x;
-        bool mv = false;
-        if (i < n) {
-            const uint32_t cur = idx[i];
-            if (cur != new_idx && cur < tab.n_total && nn.y) {
-                bool dead;
-                const uint64_t key = __ldg(keys + i);
-                mv = join_wins(key, cur, new_idx, nn, by_idx, &dead);
-                uint32_t to = new_idx;
-                if (dead) { to = hrw_scalar(key, tab); mv = to != cur; }   // rare: incumbent not live
-                if (mv) { idx[i] = to; if (counters) { atomicSub(&counters[cur], 1u); if (to != kNone) atomicAdd(&counters[to], 1u); } }
-            }
-        }
-        warp_add(moved, mv);
-    }
+// One object of a join: returns the node it belongs on afterwards (== cur when nothing changes).
+__device__ __forceinline__ uint32_t join_target(uint64_t key, uint32_t cur, uint32_t new_idx, const uint4 nn, const uint4 *by_idx, const NodeTabDev &tab) {
+    if (cur == new_idx || cur >= tab.n_total || !nn.y) return cur;
+    bool dead;
+    if (join_wins(key, cur, new_idx, nn, by_idx, &dead)) return new_idx;
+    return dead ? hrw_scalar(key, tab) : cur;   // rare: the incumbent is not live
 }
 
+// Dense set, 12 B/object stream: each thread owns 4 consecutive objects per trip -- two 128-bit key loads and one 128-bit index
+// load, all issued before any of them is used, and the next trip's loads are in flight while this one computes.
+constexpr int kJoinOpt = 4;
+template <bool SMEM>
 __global__ void __launch_bounds__(256)
-k_dir_rebalance_join(DirDev dir, NodeTabDev tab, uint32_t new_idx, unsigned long long *moved, uint32_t smem_nodes) {
-    const uint4 *by_idx = stage_by_idx(tab, smem_nodes);
-    const uint4 *slots = reinterpret_cast<const uint4 *>(dir.slots);
+k_rebalance_join(const uint64_t *__restrict__ keys, uint32_t *__restrict__ idx, uint64_t n, NodeTabDev tab, uint32_t new_idx,
+                 uint32_t *__restrict__ counters, unsigned long long *moved) {
+    const uint4 *by_idx = stage_by_idx<SMEM>(tab);
     const uint4 nn = __ldg(tab.by_idx + new_idx);
-    const uint64_t cap = dir.mask + 1;
-    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < cap; base += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t i = base + threadIdx.x;
-        bool mv = false;
-        if (i < cap) {
-            const uint4 v = slots[i];
-            const unsigned long long key = ((unsigned long long)v.y << 32) | v.x;
-            if (key != kEmptyKey && v.z != kNone && v.z != new_idx && v.z < tab.n_total && nn.y) {
-                bool dead;
-                mv = join_wins(key, v.z, new_idx, nn, by_idx, &dead);
-                uint32_t to = new_idx;
-                if (dead) { to = hrw_scalar(key, tab); mv = to != v.z; }
-                if (mv) reinterpret_cast<uint32_t *>(&dir.slots[i].val)[0] = to;
+    const uint64_t n_quads = (n + kJoinOpt - 1) / kJoinOpt, stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long n_moved = 0;
+    ulonglong2 k0, k1;
+    uint4 cur4;
+    auto load = [&](uint64_t q) {
+        const uint64_t f = q * kJoinOpt;
+        if (f + 3 < n) {
+            k0 = __ldg(reinterpret_cast<const ulonglong2 *>(keys + f));
+            k1 = __ldg(reinterpret_cast<const ulonglong2 *>(keys + f + 2));
+            cur4 = *reinterpret_cast<const uint4 *>(idx + f);
+        } else {   // ragged tail: element by element, missing ones read as "already on the new node" (skipped)
+            k0.x = f < n ? __ldg(keys + f) : 0; k0.y = f + 1 < n ? __ldg(keys + f + 1) : 0; k1.x = f + 2 < n ? __ldg(keys + f + 2) : 0; k1.y = 0;
+            cur4.x = f < n ? idx[f] : new_idx; cur4.y = f + 1 < n ? idx[f + 1] : new_idx; cur4.z = f + 2 < n ? idx[f + 2] : new_idx; cur4.w = new_idx;
+        }
+    };
+    uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n_quads) load(q);
+    for (; q < n_quads; q += stride) {
+        const ulonglong2 a0 = k0, a1 = k1;
+        const uint4 c = cur4;
+        if (q + stride < n_quads) load(q + stride);
+        uint4 t;
+        t.x = join_target(a0.x, c.x, new_idx, nn, by_idx, tab);
+        t.y = join_target(a0.y, c.y, new_idx, nn, by_idx, tab);
+        t.z = join_target(a1.x, c.z, new_idx, nn, by_idx, tab);
+        t.w = join_target(a1.y, c.w, new_idx, nn, by_idx, tab);
+        const uint32_t tt[4] = {t.x, t.y, t.z, t.w}, cc[4] = {c.x, c.y, c.z, c.w};
+        uint32_t changed = 0;
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            if (tt[e] != cc[e]) {
+                changed++;
+                if (q * kJoinOpt + e < n) idx[q * kJoinOpt + e] = tt[e];
+                if (counters) { atomicSub(&counters[cc[e]], 1u); if (tt[e] != kNone) atomicAdd(&counters[tt[e]], 1u); }
             }
         }
-        warp_add(moved, mv);
+        n_moved += changed;
     }
+    warp_flush(moved, n_moved);
+}
+
+// Directory, 16 B/slot stream: four independent 128-bit slot loads per thread per trip.
+template <bool SMEM>
+__global__ void __launch_bounds__(256)
+k_dir_rebalance_join(DirDev dir, NodeTabDev tab, uint32_t new_idx, unsigned long long *moved) {
+    const uint4 *by_idx = stage_by_idx<SMEM>(tab);
+    const uint4 *slots = reinterpret_cast<const uint4 *>(dir.slots);
+    const uint4 nn = __ldg(tab.by_idx + new_idx);
+    const uint64_t cap = dir.mask + 1, stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long n_moved = 0;
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < cap; i0 += stride * 4) {
+        uint4 v[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) { const uint64_t i = i0 + e * stride; v[e] = i < cap ? slots[i] : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, kNone, 0); }
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const unsigned long long key = ((unsigned long long)v[e].y << 32) | v[e].x;
+            if (key == kEmptyKey || v[e].z == kNone) continue;
+            const uint32_t to = join_target(key, v[e].z, new_idx, nn, by_idx, tab);
+            if (to != v[e].z) { reinterpret_cast<uint32_t *>(&dir.slots[i0 + e * stride].val)[0] = to; n_moved++; }
+        }
+    }
+    warp_flush(moved, n_moved);
 }
 
 // LEAVE(gone): pick the objects recorded on the node (4 B/object scan) into a compact list ...
 __global__ void __launch_bounds__(256)
 k_select_on_node(const uint32_t *__restrict__ idx, uint64_t n, uint32_t node, uint32_t *__restrict__ sel, unsigned long long *nsel) {
-    // 128-bit loads: one thread scans 4 consecutive objects (idx is allocated 256-byte aligned)
-    const uint64_t n4 = (n + 3) / 4;
-    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n4; base += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t v = base + threadIdx.x;
-        uint32_t hits = 0;   // bit q set: object 4v+q is on the node
-        if (v < n4) {
-            uint4 x;
-            if (4 * v + 3 < n) x = __ldg(reinterpret_cast<const uint4 *>(idx) + v);
-            else { x.x = __ldg(idx + 4 * v); x.y = 4 * v + 1 < n ? __ldg(idx + 4 * v + 1) : ~node; x.z = 4 * v + 2 < n ? __ldg(idx + 4 * v + 2) : ~node; x.w = ~node; }
-            hits = (x.x == node) | ((x.y == node) << 1) | ((x.z == node) << 2) | ((x.w == node) << 3);
+    // 128-bit loads, four of them in flight per thread: one thread scans 4 x 4 objects per trip (idx is 256-byte aligned)
+    const uint64_t n4 = (n + 3) / 4, stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n4; base += stride * 4) {
+        uint4 x[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const uint64_t v = base + e * stride + threadIdx.x;
+            if (v < n4 && 4 * v + 3 < n) x[e] = __ldg(reinterpret_cast<const uint4 *>(idx) + v);
+            else if (v < n4) { x[e].x = __ldg(idx + 4 * v); x[e].y = 4 * v + 1 < n ? __ldg(idx + 4 * v + 1) : ~node; x[e].z = 4 * v + 2 < n ? __ldg(idx + 4 * v + 2) : ~node; x[e].w = ~node; }
+            else x[e] = make_uint4(~node, ~node, ~node, ~node);
         }
-        const unsigned m = __ballot_sync(0xFFFFFFFFu, hits != 0);
-        if (m) {                                        // rare: about 4/M of the vectors
-            const unsigned lane = threadIdx.x & 31;
-            const uint32_t mine = __popc(hits);
-            uint32_t pre = mine;                        // inclusive warp prefix sum of the hit counts
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, pre, o); if (lane >= (unsigned)o) pre += t; }
-            const uint32_t total = __shfl_sync(0xFFFFFFFFu, pre, 31);
-            unsigned long long b = 0;
-            if (lane == 0) b = atomicAdd(nsel, (unsigned long long)total);
-            b = __shfl_sync(0xFFFFFFFFu, b, 0) + (pre - mine);
+        for (int e = 0; e < 4; e++) {
+            const uint64_t v = base + e * stride + threadIdx.x;
+            const uint32_t hits = (x[e].x == node) | ((x[e].y == node) << 1) | ((x[e].z == node) << 2) | ((x[e].w == node) << 3);   // bit q: object 4v+q is on the node
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, hits != 0);
+            if (m) {                                        // rare: about 4/M of the vectors
+                const unsigned lane = threadIdx.x & 31;
+                const uint32_t mine = __popc(hits);
+                uint32_t pre = mine;                        // inclusive warp prefix sum of the hit counts
 #pragma unroll
-            for (int q = 0; q < 4; q++) if (hits >> q & 1) sel[b++] = (uint32_t)(4 * v + q);
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, pre, o); if (lane >= (unsigned)o) pre += t; }
+                const uint32_t total = __shfl_sync(0xFFFFFFFFu, pre, 31);
+                unsigned long long b = 0;
+                if (lane == 0) b = atomicAdd(nsel, (unsigned long long)total);
+                b = __shfl_sync(0xFFFFFFFFu, b, 0) + (pre - mine);
+#pragma unroll
+                for (int qq = 0; qq < 4; qq++) if (hits >> qq & 1) sel[b++] = (uint32_t)(4 * v + qq);
+            }
         }
     }
 }
@@ -431,7 +473,6 @@ __global__ void k_gather_keys(const uint64_t *__restrict__ keys, const uint32_t 
 // signal: a release store of the epoch into flags[rank] of every peer; wait: spin (acquire loads, system scope) until my
 // own window carries this epoch from every rank; sum.  Slots are double buffered by epoch parity: nobody can be two
 // exchanges ahead, because every exchange needs everybody's flag.
-struct XchgPeers { uint32_t *win[16]; };
 __global__ void __launch_bounds__(1024)
 k_exchange_p2p(const uint32_t *__restrict__ local, XchgPeers peers, uint32_t rank, uint32_t world, uint32_t M, uint32_t max_nodes, uint32_t epoch,
                uint32_t *__restrict__ out_global) {
@@ -461,70 +502,14 @@ k_exchange_p2p(const uint32_t *__restrict__ local, XchgPeers peers, uint32_t ran
     }
 }
 
-// The counter exchange AND the bounded-load capacity check of a pass as one single-CTA kernel: exchange as
-// above (skipped when world == 1), then per node  over = live && count > cap,  thr = floor(2^32 (count - cap) / count),
-// closed |= over, and two words for the host in mapped pinned memory: {any node over, live nodes still open}.  The host
-// reads 8 bytes after the stream synchronises; the M-wide counter vector never crosses PCIe unless a spill round follows.
+// The counter exchange AND the bounded-load capacity check of a pass as one single-CTA kernel (bounded_tail.cuh)
 __global__ void __launch_bounds__(1024)
-k_exchange_check(const uint32_t *__restrict__ local, XchgPeers peers, uint32_t rank, uint32_t world, uint32_t M, uint32_t max_nodes, uint32_t epoch,
-                 uint32_t *__restrict__ out_global, const uint32_t *__restrict__ cap, const uint8_t *__restrict__ node_state, uint8_t *__restrict__ closed,
-                 uint32_t *__restrict__ thr, uint8_t *__restrict__ over, volatile uint32_t *host_flags) {
-    __shared__ uint32_t s_any, s_open;
-    if (threadIdx.x == 0) { s_any = 0; s_open = 0; }
-    if (world > 1) {
-        const size_t slot_words = (size_t)2 * world * max_nodes;
-        const size_t par = (size_t)(epoch & 1u) * world * max_nodes;
-        for (uint32_t p = 0; p < world; p++) {
-            uint32_t *dst = peers.win[p] + par + (size_t)rank * max_nodes;
-            for (uint32_t j = threadIdx.x; j < M; j += blockDim.x) dst[j] = local[j];
-        }
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x < world) {
-            uint32_t *flag = peers.win[threadIdx.x] + slot_words + rank;
-            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
-            const uint32_t *mine = peers.win[rank] + slot_words + threadIdx.x;
-            uint32_t v;
-            do { asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory"); } while ((int32_t)(v - epoch) < 0);
-        }
-        __syncthreads();
-        const uint32_t *src = peers.win[rank] + par;
-        for (uint32_t j = threadIdx.x; j < M; j += blockDim.x) {
-            uint32_t sum = 0;
-            for (uint32_t r = 0; r < world; r++) sum += src[(size_t)r * max_nodes + j];
-            out_global[j] = sum;
-        }
-    } else {
-        __syncthreads();
-        if (local != out_global)
-            for (uint32_t j = threadIdx.x; j < M; j += blockDim.x) out_global[j] = local[j];
-    }
-    uint32_t my_any = 0, my_open = 0;
-    for (uint32_t j = threadIdx.x; j < M; j += blockDim.x) {      // same thread wrote out_global[j] above
-        const bool live = node_state[j] & kNodeLive;
-        const uint32_t c = out_global[j], cp = cap[j];
-        const bool ov = live && c > cp;
-        over[j] = ov;
-        thr[j] = ov ? (uint32_t)((((unsigned long long)(c - cp)) << 32) / c) : 0u;
-        if (ov) closed[j] = 1;
-        my_any |= ov;
-        my_open += live && !closed[j];
-    }
-    if (my_any) atomicOr(&s_any, 1u);
-    if (my_open) atomicAdd(&s_open, my_open);
-    __syncthreads();
-    if (threadIdx.x == 0) { host_flags[0] = s_any; host_flags[1] = s_open; __threadfence_system(); }
-}
+k_exchange_check(const uint32_t *__restrict__ local, BoundedTail b) { exchange_and_check_block(b, local); }
 
 }  // namespace
 
-void launch_exchange_check(const Launch &L, const uint32_t *d_local, uint32_t *const *peer_windows, uint32_t rank, uint32_t world, uint32_t M, uint32_t max_nodes,
-                           uint32_t epoch, uint32_t *d_out_global, const uint32_t *d_cap, const uint8_t *d_node_state, uint8_t *d_closed, uint32_t *d_thr,
-                           uint8_t *d_over, uint32_t *host_flags_mapped) {
-    XchgPeers P{};
-    if (peer_windows) for (uint32_t p = 0; p < world && p < 16; p++) P.win[p] = peer_windows[p];
-    k_exchange_check<<<1, 1024, 0, L.stream>>>(d_local, P, rank, peer_windows ? world : 1u, M, max_nodes, epoch, d_out_global, d_cap, d_node_state, d_closed, d_thr,
-                                               d_over, host_flags_mapped);
+void launch_exchange_check(const Launch &L, const uint32_t *d_local, const BoundedTail &b) {
+    k_exchange_check<<<1, 1024, 0, L.stream>>>(d_local, b);
     RIO_COUNT_LAUNCH(L);
 }
 
@@ -573,8 +558,13 @@ void launch_dir_count(const Launch &L, const DirDev &dir, unsigned long long *d_
 }
 void launch_dir_rebalance_join(const Launch &L, const DirDev &dir, const NodeTabDev &tab, uint32_t new_idx, unsigned long long *d_moved) {
     const uint32_t sn = tab.n_total <= 6144 ? tab.n_total : 0;   // 96 KB of node records at most
-    cudaFuncSetAttribute(k_dir_rebalance_join, cudaFuncAttributeMaxDynamicSharedMemorySize, 6144 * 16);
-    k_dir_rebalance_join<<<grid_for(dir.mask + 1, 256, L.sm_count, sn > 2048 ? 2 : 8), 256, (size_t)sn * 16, L.stream>>>(dir, tab, new_idx, d_moved, sn);
+    const int grid = grid_for((dir.mask + 1 + 3) / 4, 256, L.sm_count, sn > 2048 ? 2 : 8);
+    if (sn) {
+        cudaFuncSetAttribute(k_dir_rebalance_join<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6144 * 16);
+        k_dir_rebalance_join<true><<<grid, 256, (size_t)sn * 16, L.stream>>>(dir, tab, new_idx, d_moved);
+    } else {
+        k_dir_rebalance_join<false><<<grid, 256, 0, L.stream>>>(dir, tab, new_idx, d_moved);
+    }
     RIO_COUNT_LAUNCH(L);
 }
 void launch_dir_rebalance_leave(const Launch &L, const DirDev &dir, const NodeTabDev &tab, uint32_t gone_idx, unsigned long long *d_moved) {
@@ -585,13 +575,18 @@ void launch_rebalance_join(const Launch &L, const uint64_t *d_keys, uint32_t *d_
                            uint32_t *d_counters, unsigned long long *d_moved) {
     if (!n) return;
     const uint32_t sn = tab.n_total <= 6144 ? tab.n_total : 0;
-    cudaFuncSetAttribute(k_rebalance_join, cudaFuncAttributeMaxDynamicSharedMemorySize, 6144 * 16);
-    k_rebalance_join<<<grid_for(n, 256, L.sm_count, sn > 2048 ? 2 : 8), 256, (size_t)sn * 16, L.stream>>>(d_keys, d_idx, n, tab, new_idx, d_counters, d_moved, sn);
+    const int grid = grid_for((n + kJoinOpt - 1) / kJoinOpt, 256, L.sm_count, sn > 2048 ? 2 : 8);
+    if (sn) {
+        cudaFuncSetAttribute(k_rebalance_join<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6144 * 16);
+        k_rebalance_join<true><<<grid, 256, (size_t)sn * 16, L.stream>>>(d_keys, d_idx, n, tab, new_idx, d_counters, d_moved);
+    } else {
+        k_rebalance_join<false><<<grid, 256, 0, L.stream>>>(d_keys, d_idx, n, tab, new_idx, d_counters, d_moved);
+    }
     RIO_COUNT_LAUNCH(L);
 }
 void launch_select_on_node(const Launch &L, const uint32_t *d_idx, uint64_t n, uint32_t node, uint32_t *d_sel, unsigned long long *d_nsel) {
     if (!n) return;
-    k_select_on_node<<<grid_for((n + 3) / 4, 256, L.sm_count, 8), 256, 0, L.stream>>>(d_idx, n, node, d_sel, d_nsel);
+    k_select_on_node<<<grid_for((n + 15) / 16, 256, L.sm_count, 8), 256, 0, L.stream>>>(d_idx, n, node, d_sel, d_nsel);
     RIO_COUNT_LAUNCH(L);
 }
 void launch_select_spill(const Launch &L, const uint64_t *d_keys, const uint32_t *d_idx, uint64_t n, const uint32_t *d_thr, const uint8_t *d_over,

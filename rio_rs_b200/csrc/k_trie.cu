@@ -11,6 +11,7 @@
 // 128-bit load; node indices leave as 64-bit stores.
 #include "kernels.cuh"
 #include "spec.cuh"
+#include "bounded_tail.cuh"
 
 namespace rio {
 
@@ -125,7 +126,7 @@ __device__ __forceinline__ TrieSmem trie_stage(const TrieDev &t, uint32_t hist_b
 template <int BITS, int OPT, int MODE, bool SMEM>
 __global__ void __launch_bounds__(kTrieThreads, SMEM ? 5 : 3)
 k_assign_trie(const uint64_t *__restrict__ keys, uint64_t n, TrieDev t, uint32_t *__restrict__ out_idx, uint32_t *__restrict__ counters,
-              uint32_t hist_bins, unsigned long long *__restrict__ moved) {
+              uint32_t hist_bins, unsigned long long *__restrict__ moved, const __grid_constant__ BoundedTail tail) {
     static_assert(OPT % 2 == 0, "two objects per 128-bit load");
     constexpr bool in_smem = SMEM;
     const TrieSmem s = trie_stage<SMEM>(t, hist_bins);
@@ -232,6 +233,20 @@ k_assign_trie(const uint64_t *__restrict__ keys, uint64_t n, TrieDev t, uint32_t
         __syncthreads();
         for (uint32_t j = threadIdx.x; j < hist_bins; j += blockDim.x) { const uint32_t v = s.hist[j]; if (v) atomicAdd(&counters[j], v); }
     }
+    if (MODE == 0 && tail.enabled) {
+        // the pass's exchange + capacity check, in whichever CTA finishes last: its atomics on `counters` are ordered before its
+        // ticket, and the last CTA reads the counters through L2 after taking the last ticket
+        __shared__ uint32_t s_last;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = atomicAdd(tail.ticket, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (s_last) {
+            if (threadIdx.x == 0) *tail.ticket = 0;
+            __threadfence();
+            exchange_and_check_block(tail, counters);
+        }
+    }
 }
 
 // ---- gathered assign (a compact list of object positions: bounded-load spill rounds, place_batch) ---------------
@@ -314,12 +329,20 @@ uint64_t trie_wave_objects(int sm_count) { return (uint64_t)sm_count * 5 * kTrie
 
 #define RIO_TRIE_LAUNCH(KERNEL, GRID, SMEM, ...)                                                                       \
     do {                                                                                                               \
-        cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrieSmemBudget + 1024);        \
+        static bool attr_set[64] = {};   /* per device; the attribute call costs ~1 us of host time per launch otherwise */ \
+        int dev__ = 0;                                                                                                 \
+        cudaGetDevice(&dev__);                                                                                         \
+        if (dev__ < 0 || dev__ >= 64 || !attr_set[dev__]) {                                                            \
+            cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrieSmemBudget + 1024);    \
+            if (dev__ >= 0 && dev__ < 64) attr_set[dev__] = true;                                                      \
+        }                                                                                                              \
         KERNEL<<<(GRID), kTrieThreads, (SMEM), L.stream>>>(__VA_ARGS__);                                               \
     } while (0)
 
 void launch_assign_trie(const Launch &L, const uint64_t *d_keys, uint64_t n, const TrieDev &t, uint32_t *d_out_idx, uint32_t *d_counters,
-                        const uint32_t *d_sel, uint64_t n_sel, uint32_t n_total) {
+                        const uint32_t *d_sel, uint64_t n_sel, uint32_t n_total, const BoundedTail *tail) {
+    BoundedTail no_tail{};
+    const BoundedTail &tl = tail ? *tail : no_tail;
     const uint64_t n_work = d_sel ? n_sel : n;
     if (!n_work) return;
     if (d_sel) {
@@ -333,9 +356,9 @@ void launch_assign_trie(const Launch &L, const uint64_t *d_keys, uint64_t n, con
         const TrieLaunchShape sh = trie_shape(t, d_counters != nullptr, n_total, 5);
         const uint64_t tiles = (n_work + (uint64_t)kTrieThreads * OPT - 1) / ((uint64_t)kTrieThreads * OPT), cap = (uint64_t)L.sm_count * sh.ctas_per_sm;
         const int grid = (int)(tiles < cap ? tiles : cap);
-        if (!sh.in_smem) RIO_TRIE_LAUNCH((k_assign_trie<0, OPT, 0, false>), grid, sh.smem, d_keys, n_work, t, d_out_idx, d_counters, sh.hist_bins, nullptr);
-        else if (t.bits == 12) RIO_TRIE_LAUNCH((k_assign_trie<12, OPT, 0, true>), grid, sh.smem, d_keys, n_work, t, d_out_idx, d_counters, sh.hist_bins, nullptr);
-        else RIO_TRIE_LAUNCH((k_assign_trie<0, OPT, 0, true>), grid, sh.smem, d_keys, n_work, t, d_out_idx, d_counters, sh.hist_bins, nullptr);
+        if (!sh.in_smem) RIO_TRIE_LAUNCH((k_assign_trie<0, OPT, 0, false>), grid, sh.smem, d_keys, n_work, t, d_out_idx, d_counters, sh.hist_bins, nullptr, tl);
+        else if (t.bits == 12) RIO_TRIE_LAUNCH((k_assign_trie<12, OPT, 0, true>), grid, sh.smem, d_keys, n_work, t, d_out_idx, d_counters, sh.hist_bins, nullptr, tl);
+        else RIO_TRIE_LAUNCH((k_assign_trie<0, OPT, 0, true>), grid, sh.smem, d_keys, n_work, t, d_out_idx, d_counters, sh.hist_bins, nullptr, tl);
     }
     RIO_COUNT_LAUNCH(L);
 }
@@ -348,9 +371,9 @@ void launch_reassign_trie(const Launch &L, const uint64_t *d_keys, uint64_t n, c
  const TrieLaunchShape sh = trie_shape(t, d_counters != nullptr, n_total, 5);
     const uint64_t tiles = (n + (uint64_t)kTrieThreads * OPT - 1) / ((uint64_t)kTrieThreads * OPT), cap = (uint64_t)L.sm_count * sh.ctas_per_sm;
     const int grid = (int)(tiles < cap ? tiles : cap);
-    if (!sh.in_smem) RIO_TRIE_LAUNCH((k_assign_trie<0, OPT, 1, false>), grid, sh.smem, d_keys, n, t, d_idx, d_counters, sh.hist_bins, d_moved);
-    else if (t.bits == 12) RIO_TRIE_LAUNCH((k_assign_trie<12, OPT, 1, true>), grid, sh.smem, d_keys, n, t, d_idx, d_counters, sh.hist_bins, d_moved);
-    else RIO_TRIE_LAUNCH((k_assign_trie<0, OPT, 1, true>), grid, sh.smem, d_keys, n, t, d_idx, d_counters, sh.hist_bins, d_moved);
+    if (!sh.in_smem) RIO_TRIE_LAUNCH((k_assign_trie<0, OPT, 1, false>), grid, sh.smem, d_keys, n, t, d_idx, d_counters, sh.hist_bins, d_moved, BoundedTail{});
+    else if (t.bits == 12) RIO_TRIE_LAUNCH((k_assign_trie<12, OPT, 1, true>), grid, sh.smem, d_keys, n, t, d_idx, d_counters, sh.hist_bins, d_moved, BoundedTail{});
+    else RIO_TRIE_LAUNCH((k_assign_trie<0, OPT, 1, true>), grid, sh.smem, d_keys, n, t, d_idx, d_counters, sh.hist_bins, d_moved, BoundedTail{});
     RIO_COUNT_LAUNCH(L);
 }
 

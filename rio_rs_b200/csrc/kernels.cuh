@@ -57,6 +57,25 @@ struct DirDev {
 
 struct Launch { cudaStream_t stream; int sm_count; uint64_t *launch_counter; };
 
+// ---- the tail of a bounded-load pass: counter exchange + capacity check (bounded_tail.cuh) ----------------------------------
+struct XchgPeers { uint32_t *win[16]; };
+struct BoundedTail {
+    uint32_t enabled;          // 0: plain assignment, nothing below is read
+    uint32_t M;                // interned nodes (length of every per-node array)
+    uint32_t *ticket;          // CTA-done counter of the fused form (left at 0 by the last CTA)
+    uint32_t *next_zero;       // nullable: counter buffer of the next pass, cleared by the check
+    XchgPeers peers;           // world > 1: every rank's exchange window (CUDA IPC)
+    uint32_t rank, world, max_nodes, xchg_epoch;
+    uint32_t *glob;            // out: global counters
+    const uint32_t *cap;       // capacity per node
+    const uint8_t *state;      // kNodeLive per node
+    uint32_t *closed_epoch;    // closed[j] <=> closed_epoch[j] == call_epoch (no memset between calls)
+    uint32_t call_epoch;
+    uint32_t *thr;             // out: spill thresholds
+    uint8_t *over;             // out: over-capacity flags
+    volatile uint32_t *host_flags;   // mapped pinned: {any over, open nodes}
+};
+
 // solver
 void launch_assign_hrw(const Launch &L, const uint64_t *d_keys, uint64_t n, const NodeTabDev &tab, uint32_t *d_out_idx,
                        uint32_t *d_counters /*nullable, n_total entries*/, const uint32_t *d_sel /*nullable*/, uint64_t n_sel);
@@ -102,8 +121,9 @@ void launch_dir_rebalance_join(const Launch &L, const DirDev &dir, const NodeTab
 void launch_dir_rebalance_leave(const Launch &L, const DirDev &dir, const NodeTabDev &tab, uint32_t gone_idx, unsigned long long *d_moved);
 
 // HRW2 launchers; DirDev-based one is the directory-wide eager rebalance
+// tail (nullable, dense form only): the pass's exchange + capacity check runs in the last CTA of the walk kernel
 void launch_assign_trie(const Launch &L, const uint64_t *d_keys, uint64_t n, const TrieDev &t, uint32_t *d_out_idx, uint32_t *d_counters /*nullable*/,
-                        const uint32_t *d_sel /*nullable*/, uint64_t n_sel, uint32_t n_total);
+                        const uint32_t *d_sel /*nullable*/, uint64_t n_sel, uint32_t n_total, const BoundedTail *tail = nullptr);
 void launch_reassign_trie(const Launch &L, const uint64_t *d_keys, uint64_t n, const TrieDev &t, uint32_t *d_idx, uint32_t *d_counters /*nullable*/,
                           uint32_t n_total, unsigned long long *d_moved);
 void launch_dir_reassign_trie(const Launch &L, const DirDev &dir, const TrieDev &t, unsigned long long *d_moved);
@@ -121,10 +141,8 @@ void launch_gather_keys(const Launch &L, const uint64_t *d_keys, const uint32_t 
                         uint32_t *d_out_idx);
 void launch_exchange_p2p(const Launch &L, const uint32_t *d_local, uint32_t *const *peer_windows, uint32_t rank, uint32_t world, uint32_t M, uint32_t max_nodes,
                          uint32_t epoch, uint32_t *d_out_global);
-// exchange (world > 1, peer windows given) + bounded-load capacity check in one launch; host_flags_mapped = 2 u32 in mapped pinned memory
-void launch_exchange_check(const Launch &L, const uint32_t *d_local, uint32_t *const *peer_windows /*nullable*/, uint32_t rank, uint32_t world, uint32_t M,
-                           uint32_t max_nodes, uint32_t epoch, uint32_t *d_out_global, const uint32_t *d_cap, const uint8_t *d_node_state, uint8_t *d_closed,
-                           uint32_t *d_thr, uint8_t *d_over, uint32_t *host_flags_mapped);
+// exchange (world > 1) + bounded-load capacity check as its own single-CTA launch (the flat rendezvous passes and the NCCL path)
+void launch_exchange_check(const Launch &L, const uint32_t *d_local, const BoundedTail &b);
 void launch_sum_gathered(const Launch &L, const uint32_t *d_gathered, uint32_t world, uint32_t M, uint32_t *d_out);
 void launch_l2_flush(const Launch &L, uint32_t *d_buf, uint64_t n_words, uint32_t v);
 

@@ -100,8 +100,10 @@ RIO_HD uint32_t contest_u(ObjHash o, uint32_t s0, uint32_t m2, uint32_t h2) {
 inline uint64_t level_seed(uint32_t level) { return mix64(kGolden64 * ((uint64_t)level + 1) ^ kSaltLevel); }
 // T3 of a contest between a left part of weight wl and a right part of weight wr
 inline uint32_t contest_t3(uint64_t wl, uint64_t wr) {
-    if (wl + wr == 0 || wl == 0) return 0u;
-    const uint64_t t = (uint64_t)((((unsigned __int128)wl) << 31) / (wl + wr));   // <= 2^31
+    if (wl == 0) return 0u;                      // never LEFT (also the empty subtree)
+    if (wr == 0) return 0xFFFFFFFFu;             // T = 2^31: always LEFT
+    const uint64_t t = wl < (1ull << 33) ? (wl << 31) / (wl + wr)                                    // the common case fits 64 bits
+                                         : (uint64_t)((((unsigned __int128)wl) << 31) / (wl + wr));   // <= 2^31
     return t ? (uint32_t)(2 * t - 1) : 0u;
 }
 

@@ -22,7 +22,8 @@ struct NoServersAvailable : std::runtime_error {   // ClientError::NoServersAvai
 
 class FirstHop {
   public:
-    explicit FirstHop(size_t cache_size = 1000) : cache_size_(cache_size) {}   // LruCache limit, client/mod.rs:137
+    // LruCache limit, client/mod.rs:137; policy / trie_bits mirror the servers' solver (RIO_CLIENT_POLICY_*)
+    explicit FirstHop(size_t cache_size = 1000, uint32_t policy = RIO_CLIENT_POLICY_HRW, uint32_t trie_bits = 0) : cache_size_(cache_size), policy_(policy), trie_bits_(trie_bits) {}
     ~FirstHop() { rio_client_ring_destroy(ring_); }
     FirstHop(const FirstHop &) = delete;
     FirstHop &operator=(const FirstHop &) = delete;
@@ -36,6 +37,7 @@ class FirstHop {
         rio_client_ring *r = nullptr;
         if (rio_client_ring_create(p.data(), l.data(), weights.empty() ? nullptr : weights.data(), (uint32_t)addresses.size(), &r) != RIO_CLIENT_OK)
             throw std::runtime_error("rio_client_ring_create failed");
+        if (rio_client_ring_set_policy(r, policy_, trie_bits_) != RIO_CLIENT_OK) { rio_client_ring_destroy(r); throw std::runtime_error("rio_client_ring_set_policy failed"); }
         rio_client_ring_destroy(ring_);
         ring_ = r;
         addresses_ = addresses;
@@ -76,6 +78,7 @@ class FirstHop {
     rio_client_ring *ring_ = nullptr;
     std::vector<std::string> addresses_;
     size_t cache_size_;
+    uint32_t policy_ = RIO_CLIENT_POLICY_HRW, trie_bits_ = 0;
     std::list<std::pair<Key, std::string>> lru_;
     std::map<Key, std::list<std::pair<Key, std::string>>::iterator> index_;
 };

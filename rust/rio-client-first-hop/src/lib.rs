@@ -22,6 +22,7 @@ pub const RIO_CLIENT_NONE: u32 = 0xFFFF_FFFF;
 extern "C" {
     pub fn rio_client_ring_create(addresses: *const *const c_char, address_lens: *const size_t, weights: *const u32, n: u32, out: *mut *mut rio_client_ring) -> i32;
     pub fn rio_client_ring_destroy(ring: *mut rio_client_ring);
+    pub fn rio_client_ring_set_policy(ring: *mut rio_client_ring, policy: u32, trie_bits: u32) -> i32;
     pub fn rio_client_ring_size(ring: *const rio_client_ring) -> u32;
     pub fn rio_client_ring_address(ring: *const rio_client_ring, index: u32, buf: *mut c_char, cap: size_t, out_len: *mut size_t) -> i32;
     pub fn rio_client_object_key(ty: *const c_char, ty_len: size_t, id: *const c_char, id_len: size_t) -> u64;

@@ -117,3 +117,25 @@ def test_cpp_mirror_conformance(tmp_path):
                            "-L" + libdir, "-lrio_client", "-Wl,-rpath," + libdir])
     r = subprocess.run([exe, str(tmp_path / "nodes.txt"), str(tmp_path / "ids.txt")], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0 and "all passed" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("bits", [0, 12, 4])
+def test_first_hop_hrw2_equals_the_oracle_and_ignores_listing_order(oracle, bits):
+    """The client under the hierarchical policy picks the oracle's node for every id, also after a node left,
+    and -- positions and chains being ordered by a hash of the address -- independently of the order it lists the servers in."""
+    from rio_rs_b200 import client as CL
+
+    addrs, seeds, w = oracle.synth_nodes(200)
+    w[5] = 0
+    keys = oracle.synth_keys(20000, 4)
+    fh = CL.FirstHop(addrs, w, policy="hrw2", trie_bits=bits)
+    want = oracle.assign_hrw2(keys, seeds, w, bits=bits or 12)
+    assert (fh.first_hop_batch(keys) == want).all()
+    perm = np.random.default_rng(3).permutation(200)
+    fh2 = CL.FirstHop([addrs[j] for j in perm], w[perm], policy="hrw2", trie_bits=bits)
+    assert (perm[fh2.first_hop_batch(keys)] == want).all()
+    w2 = w.copy()
+    w2[9] = 0
+    fh.set_active_servers(addrs, w2)
+    assert (fh.first_hop_batch(keys) == oracle.assign_hrw2(keys, seeds, w2, bits=bits or 12)).all()
+    assert CL.FirstHop([], None, policy="hrw2").first_hop_batch(keys[:5]).tolist() == [CL.NONE] * 5

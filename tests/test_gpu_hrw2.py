@@ -222,3 +222,27 @@ def test_full_size_10m_x_1024_every_object(gp, oracle):
     assert s.rebalance("join", 17) == moved and (s.read() == idx).all()
     # same result through the host-buffer API (H2D/D2H pipelined path)
     assert (p.assign_batch(keys[:3_000_000]) == idx[:3_000_000]).all()
+
+
+def test_client_first_hop_reaches_the_owner_without_redirect(gp, oracle):
+    """SURVEY 8(f) row 2 under HRW2: ids the servers placed with policy "hrw2" are found by the client's own walk of the same
+    trie (include/rio_client.h), node for node, also after a node left."""
+    from rio_rs_b200 import client as CL
+
+    try:
+        CL.lib()
+    except Exception as e:
+        pytest.skip("librio_client.so unavailable: %r" % (e,))
+    p = provider(gp)
+    addrs, seeds, w = oracle.synth_nodes(64)
+    p.set_nodes(addrs, w)
+    keys = oracle.synth_keys(30000, 6)
+    owner = p.place_batch(keys, "hrw2")
+    fh = CL.FirstHop(addrs, w, policy="hrw2")
+    assert (fh.first_hop_batch(keys) == owner).all()
+    p.node_set_active(9, False)
+    p.rebalance("leave", 9)
+    w2 = w.copy()
+    w2[9] = 0
+    fh.set_active_servers(addrs, w2)
+    assert (fh.first_hop_batch(keys) == p.lookup_many(keys)).all()

@@ -722,9 +722,10 @@ def test_exact_ties_go_to_the_lowest_index_on_the_gpu(gp, oracle, variant, mode)
         got = p.assign_batch(keys)
         want = oracle.assign_hrw(keys, seeds, w, threads=8)
         assert (got == want).all()
-        # the ties really happened: the upper twin never wins although it scores exactly like the lower one
+        # the ties really happened: the upper twin never wins although it scores exactly like the lower one (twins hash alike, so
+        # the pair wins as often as ONE node does)
         for a, b in twins:
-            assert (want != b).all() and (want == a).sum() > (1.2 * len(keys) / M if M < 1000 else 0)
+            assert (want != b).all() and (want == a).sum() > (0.6 * len(keys) / M if M < 1000 else 0)
         assert (want != 6).all() and (want != 7).all()
     finally:
         os.environ.pop("RIO_ASSIGN_VARIANT", None)
