@@ -539,6 +539,10 @@ def main():
             del t, q
             if rank == 0 and world == 1:
                 extra.update(extra_configs(p, O, n))
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import bench_c1
+
+                extra["C1_per_id_lookup_1k_ids_4_nodes"] = bench_c1.run(R, O, device=local_rank)
         except Exception as e:  # the headline line must still be printed
             extra["error"] = repr(e)
 

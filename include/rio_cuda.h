@@ -237,6 +237,15 @@ void        rio_cuda_resolver_destroy(rio_resolver *r);
 rio_status  rio_cuda_resolver_resolve(rio_resolver *r, uint64_t key, uint32_t *out_idx);
 rio_status  rio_cuda_resolver_resolve_str(rio_resolver *r, const char *type, size_t type_len, const char *id, size_t id_len,
                                           char *buf, size_t cap, size_t *out_len);
+/* The trait's own per-id calls through the same queue (lookup / update / remove, mod.rs:46-55): concurrent callers share one
+ * GPU round trip.  Inside one micro-batch the updates are applied first (in submission order), then the lookups, then the
+ * resolves.  update with idx == RIO_NONE (or address == NULL) is update(None) = remove. */
+rio_status  rio_cuda_resolver_lookup(rio_resolver *r, uint64_t key, uint32_t *out_idx);
+rio_status  rio_cuda_resolver_update(rio_resolver *r, uint64_t key, uint32_t idx);
+rio_status  rio_cuda_resolver_lookup_str(rio_resolver *r, const char *type, size_t type_len, const char *id, size_t id_len,
+                                         char *buf, size_t cap, size_t *out_len);
+rio_status  rio_cuda_resolver_update_str(rio_resolver *r, const char *type, size_t type_len, const char *id, size_t id_len,
+                                         const char *address, size_t address_len);
 rio_status  rio_cuda_resolver_stats(rio_resolver *r, uint64_t *calls, uint64_t *batches, uint64_t *largest_batch);
 const char *rio_cuda_resolver_last_error(void);
 

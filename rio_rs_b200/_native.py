@@ -93,6 +93,10 @@ SIGNATURES = {
     "rio_cuda_resolver_destroy": (None, [H]),
     "rio_cuda_resolver_resolve": (C.c_int32, [H, C.c_uint64, u32p]),
     "rio_cuda_resolver_resolve_str": (C.c_int32, [H, C.c_char_p, sz, C.c_char_p, sz, C.c_char_p, sz, C.POINTER(sz)]),
+    "rio_cuda_resolver_lookup": (C.c_int32, [H, C.c_uint64, u32p]),
+    "rio_cuda_resolver_update": (C.c_int32, [H, C.c_uint64, C.c_uint32]),
+    "rio_cuda_resolver_lookup_str": (C.c_int32, [H, C.c_char_p, sz, C.c_char_p, sz, C.c_char_p, sz, C.POINTER(sz)]),
+    "rio_cuda_resolver_update_str": (C.c_int32, [H, C.c_char_p, sz, C.c_char_p, sz, C.c_char_p, sz]),
     "rio_cuda_resolver_stats": (C.c_int32, [H, u64p, u64p, u64p]),
     "rio_cuda_resolver_last_error": (C.c_char_p, []),
     "rio_cuda_update_str": (C.c_int32, [H, C.c_char_p, sz, C.c_char_p, sz, C.c_char_p, sz]),

@@ -64,7 +64,12 @@ __device__ __forceinline__ void exchange_and_check_block(const BoundedTail &b, c
     if (my_any) atomicOr(&s_any, 1u);
     if (my_open) atomicAdd(&s_open, my_open);
     __syncthreads();
-    if (threadIdx.x == 0) { b.host_flags[0] = s_any; b.host_flags[1] = s_open; __threadfence_system(); }
+    if (threadIdx.x == 0) {   // the sequence word goes last: the host polls it instead of paying a stream-synchronise wake-up
+        b.host_flags[0] = s_any; b.host_flags[1] = s_open;
+        __threadfence_system();
+        b.host_flags[2] = b.flag_seq;
+        __threadfence_system();
+    }
 }
 
 }  // namespace rio

@@ -443,7 +443,7 @@ __global__ void k_synth_keys(uint64_t *__restrict__ keys, uint64_t first, uint64
 // the block's contiguous byte range is staged into shared memory with coalesced 16-byte loads, then each
 // thread walks its own id out of shared memory.
 constexpr int kHashThreads = 256;
-constexpr uint32_t kHashSmemBytes = 48 * 1024 - 64;
+constexpr uint32_t kHashSmemBytes = 24 * 1024 - 64;   // 8 CTAs per SM: the two barriers of a trip expose a full HBM latency, more CTAs cover it
 __global__ void __launch_bounds__(kHashThreads)
 k_hash_ids(const char *__restrict__ packed, const uint64_t *__restrict__ offsets, uint64_t n, uint64_t *__restrict__ keys) {
     __shared__ __align__(16) unsigned char sbuf[kHashSmemBytes];
@@ -606,7 +606,7 @@ void launch_synth_keys(const Launch &L, uint64_t *d_keys, uint64_t first, uint64
 
 void launch_hash_ids(const Launch &L, const char *d_packed, const uint64_t *d_offsets, uint64_t n, uint64_t *d_keys) {
     if (!n) return;
-    k_hash_ids<<<grid_for(n, kHashThreads, L.sm_count, 4), kHashThreads, 0, L.stream>>>(d_packed, d_offsets, n, d_keys);
+    k_hash_ids<<<grid_for(n, kHashThreads, L.sm_count, 8), kHashThreads, 0, L.stream>>>(d_packed, d_offsets, n, d_keys);
     RIO_COUNT_LAUNCH(L);
 }
 

@@ -73,7 +73,8 @@ struct BoundedTail {
     uint32_t call_epoch;
     uint32_t *thr;             // out: spill thresholds
     uint8_t *over;             // out: over-capacity flags
-    volatile uint32_t *host_flags;   // mapped pinned: {any over, open nodes}
+    volatile uint32_t *host_flags;   // mapped pinned: {any over, open nodes, sequence number of this check}
+    uint32_t flag_seq;
 };
 
 // solver

@@ -380,6 +380,33 @@ class Resolver:
             raise (Upstream if st == N.RIO_ERR_UPSTREAM else Unknown)(msg.decode(errors="replace") if msg else "")
         return None if n.value == C.c_size_t(-1).value else buf.raw[: n.value].decode()
 
+    def _rck(self, st):
+        if st != N.RIO_OK:
+            msg = self.L.rio_cuda_resolver_last_error()
+            raise (Upstream if st == N.RIO_ERR_UPSTREAM else Unknown)(msg.decode(errors="replace") if msg else "")
+
+    # the trait's per-id calls, coalesced with every other caller's (mod.rs:46-55)
+    def lookup(self, object_id):
+        t, i = (s.encode() for s in object_id)
+        buf = C.create_string_buffer(256)
+        n = C.c_size_t(0)
+        self._rck(self.L.rio_cuda_resolver_lookup_str(self.r, t, len(t), i, len(i), buf, 256, C.byref(n)))
+        return None if n.value == C.c_size_t(-1).value else buf.raw[: n.value].decode()
+
+    def update(self, item):
+        t, i = (s.encode() for s in item.object_id)
+        a = None if item.server_address is None else item.server_address.encode()
+        self._rck(self.L.rio_cuda_resolver_update_str(self.r, t, len(t), i, len(i), a, 0 if a is None else len(a)))
+
+    def remove(self, object_id):
+        t, i = (s.encode() for s in object_id)
+        self._rck(self.L.rio_cuda_resolver_update_str(self.r, t, len(t), i, len(i), None, 0))
+
+    def lookup_key(self, key):
+        out = C.c_uint32(0)
+        self._rck(self.L.rio_cuda_resolver_lookup(self.r, int(key), C.byref(out)))
+        return out.value
+
     def stats(self):
         a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
         self.L.rio_cuda_resolver_stats(self.r, C.byref(a), C.byref(b), C.byref(c))

@@ -107,6 +107,10 @@ extern "C" {
     pub fn rio_cuda_resolver_destroy(r: *mut rio_resolver);
     pub fn rio_cuda_resolver_resolve(r: *mut rio_resolver, key: u64, out_idx: *mut u32) -> rio_status;
     pub fn rio_cuda_resolver_resolve_str(r: *mut rio_resolver, ty: *const c_char, ty_len: size_t, id: *const c_char, id_len: size_t, buf: *mut c_char, cap: size_t, out_len: *mut size_t) -> rio_status;
+    pub fn rio_cuda_resolver_lookup(r: *mut rio_resolver, key: u64, out_idx: *mut u32) -> rio_status;
+    pub fn rio_cuda_resolver_update(r: *mut rio_resolver, key: u64, idx: u32) -> rio_status;
+    pub fn rio_cuda_resolver_lookup_str(r: *mut rio_resolver, ty: *const c_char, ty_len: usize, id: *const c_char, id_len: usize, buf: *mut c_char, cap: usize, out_len: *mut usize) -> rio_status;
+    pub fn rio_cuda_resolver_update_str(r: *mut rio_resolver, ty: *const c_char, ty_len: usize, id: *const c_char, id_len: usize, address: *const c_char, address_len: usize) -> rio_status;
     pub fn rio_cuda_resolver_stats(r: *mut rio_resolver, calls: *mut u64, batches: *mut u64, largest_batch: *mut u64) -> rio_status;
     pub fn rio_cuda_resolver_last_error() -> *const c_char;
 

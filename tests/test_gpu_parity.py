@@ -729,3 +729,55 @@ def test_exact_ties_go_to_the_lowest_index_on_the_gpu(gp, oracle, variant, mode)
         assert (want != 6).all() and (want != 7).all()
     finally:
         os.environ.pop("RIO_ASSIGN_VARIANT", None)
+
+
+def test_per_id_trait_calls_through_the_coalescing_front_end(gp, oracle):
+    """lookup / update / remove per id (mod.rs:46-55) from 16 threads through the resolver: every thread owns a slice of the
+    ids and replays a random op sequence on it; results must equal the LocalObjectPlacement restatement replaying the same
+    sequence, and the calls must have been coalesced into far fewer engine batches."""
+    import threading
+
+    p, m = provider(gp), oracle.DirectoryModel()
+    addrs = ["10.0.0.%d:5000" % j for j in range(4)]
+    p.set_nodes(addrs)
+    r = gp.Resolver(p, policy="self", self_address=addrs[0], max_batch=256, max_wait_us=100)
+    T, per = 16, 60
+    errors = []
+
+    def work(t):
+        rng = random.Random(100 + t)
+        ids = [("T%d" % t, str(i)) for i in range(per)]
+        local = {}
+        try:
+            for _ in range(300):
+                oid = rng.choice(ids)
+                x = rng.random()
+                if x < 0.4:
+                    a = rng.choice(addrs)
+                    r.update(gp.ObjectPlacementItem(gp.ObjectId(*oid), a))
+                    local[oid] = a
+                elif x < 0.5:
+                    r.remove(gp.ObjectId(*oid))
+                    local.pop(oid, None)
+                else:
+                    got = r.lookup(gp.ObjectId(*oid))
+                    if got != local.get(oid):
+                        errors.append((oid, got, local.get(oid)))
+            for oid, a in local.items():
+                m.update(oid[0], oid[1], a)
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(T)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    assert not errors, errors[:3]
+    for t in range(T):
+        for i in range(per):
+            assert p.lookup(gp.ObjectId("T%d" % t, str(i))) == m.lookup("T%d" % t, str(i))
+    assert p.directory_len()[0] == len(m)
+    st = r.stats()
+    assert st["calls"] == T * 300 and st["batches"] < st["calls"] and st["largest_batch"] > 1, st
+    r.close()

@@ -84,6 +84,26 @@ moved = s.rebalance("leave", 17)
 p2.event_record(1)
 p2.sync()
 rec("C5 leave rebalance %dM objects (k_select_on_node + k_assign_hrw_v2 on movers)" % (N // 1_000_000), p2.event_elapsed_ms(0, 1), N, "objects", 4 * N, "moved=%d" % moved)
+# the same set under HRW2: walk kernel (12 B/object), join / leave = re-walk + compare (16 B/object)
+p2.set_solver("hrw2")
+s.assign()
+rec("assign %dM x 1024 HRW2 (k_assign_trie)" % (N // 1_000_000), timed(s.assign, 5, 1, p2), N, "placements", 12 * N)
+rec("bounded pass %dM x 1024 HRW2 (k_assign_trie + fused exchange/check tail)" % (N // 1_000_000), timed(lambda: s.assign_bounded(0, 5, 4, 4), 5, 1, p2), N, "placements", 12 * N)
+p2.node_set_active(33, False)
+p2.sync()
+p2.event_record(0)
+moved = s.rebalance("leave", 33)
+p2.event_record(1)
+p2.sync()
+rec("C5 leave rebalance %dM objects HRW2 (k_assign_trie, compare mode)" % (N // 1_000_000), p2.event_elapsed_ms(0, 1), N, "objects", 16 * N, "moved=%d, includes node-table rebuild" % moved)
+p2.node_set_active(33, True)
+p2.sync()
+p2.event_record(0)
+moved = s.rebalance("join", 33)
+p2.event_record(1)
+p2.sync()
+rec("C5 join rebalance %dM objects HRW2 (k_assign_trie, compare mode)" % (N // 1_000_000), p2.event_elapsed_ms(0, 1), N, "objects", 16 * N, "moved=%d, includes node-table rebuild" % moved)
+p2.set_solver("hrw")
 del s
 
 # ---- directory ---------------------------------------------------------------------------------------------
@@ -118,6 +138,12 @@ j2 = p2.node_upsert(addrs[M + 1], int(w[M + 1]))
 t0 = time.perf_counter()
 mv = p2.rebalance("join", j2)
 rec("directory-wide join rebalance %d slots (k_dir_rebalance_join)" % slots, (time.perf_counter() - t0) * 1e3, slots, "slots", 16 * slots, "moved=%d, wall clock" % mv)
+p2.set_solver("hrw2")
+p2.node_set_active(44, False)
+t0 = time.perf_counter()
+mv = p2.rebalance("leave", 44)
+rec("directory-wide re-placement %d slots HRW2 (k_dir_reassign_trie)" % slots, (time.perf_counter() - t0) * 1e3, slots, "slots", 16 * slots, "moved=%d, wall clock" % mv)
+p2.set_solver("hrw")
 del s
 
 # ---- device-side id hashing -----------------------------------------------------------------------------------
