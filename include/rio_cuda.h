@@ -179,6 +179,13 @@ rio_status  rio_cuda_set_assign(rio_objset *s, uint32_t use_affinity);
  * n_total = global object count (0 = this set's n * world).  out_passes may be NULL. */
 rio_status  rio_cuda_set_assign_bounded(rio_objset *s, uint64_t n_total, uint32_t cap_num, uint32_t cap_den,
                                         uint32_t max_rounds, uint32_t *out_passes);
+/* The same call in two halves.  _begin enqueues pass 0 -- under RIO_SOLVER_HRW2 ONE kernel: walk, histogram, counter exchange over
+ * peer memory, capacity check -- and returns without waiting; _end waits for that check (two words in mapped pinned memory) and
+ * runs the spill rounds it asks for.  Several sets of one handle may be between _begin and _end at the same time (a set takes
+ * part in one bounded call at a time), which keeps the GPU's queue full across calls; with ranks > 1 every rank must issue its
+ * _begin / _end calls in the same order.  rio_cuda_set_assign_bounded == _begin followed by _end. */
+rio_status  rio_cuda_set_assign_bounded_begin(rio_objset *s, uint64_t n_total, uint32_t cap_num, uint32_t cap_den, uint32_t max_rounds);
+rio_status  rio_cuda_set_assign_bounded_end(rio_objset *s, uint32_t *out_passes);
 /* Incremental rebalance of the set after the node table changed (call AFTER node_upsert / node_set_active). */
 rio_status  rio_cuda_set_rebalance(rio_objset *s, uint32_t event, uint32_t idx, uint64_t *out_moved);
 /* Global (all ranks) per-node counters of the set's current assignment. */

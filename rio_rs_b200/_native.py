@@ -68,6 +68,8 @@ SIGNATURES = {
     "rio_cuda_set_load_feats": (C.c_int32, [H, vp, C.c_uint32]),
     "rio_cuda_set_assign": (C.c_int32, [H, C.c_uint32]),
     "rio_cuda_set_assign_bounded": (C.c_int32, [H, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, u32p]),
+    "rio_cuda_set_assign_bounded_begin": (C.c_int32, [H, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "rio_cuda_set_assign_bounded_end": (C.c_int32, [H, u32p]),
     "rio_cuda_set_rebalance": (C.c_int32, [H, C.c_uint32, C.c_uint32, u64p]),
     "rio_cuda_set_counters": (C.c_int32, [H, vp, C.c_uint32]),
     "rio_cuda_set_read": (C.c_int32, [H, C.c_uint64, C.c_uint64, vp, vp]),

@@ -46,28 +46,41 @@ __device__ __forceinline__ void exchange_and_check_block(const BoundedTail &b, c
         }
     } else {
         __syncthreads();
-        if (local != b.glob)
-            for (uint32_t j = threadIdx.x; j < M; j += blockDim.x) b.glob[j] = __ldcg(local + j);
     }
+    // the check: up to 4 nodes per thread per trip, every load of the trip issued before the first use (the block is alone on the
+    // machine by now: latency, not bandwidth, is what this loop costs)
+    const bool from_local = world <= 1;
     uint32_t my_any = 0, my_open = 0;
-    for (uint32_t j = threadIdx.x; j < M; j += blockDim.x) {      // the same thread wrote glob[j] above
-        const bool live = b.state[j] & kNodeLive;
-        const uint32_t c = b.glob[j], cp = b.cap[j];
-        const bool ov = live && c > cp;
-        b.over[j] = ov;
-        b.thr[j] = ov ? (uint32_t)((((unsigned long long)(c - cp)) << 32) / c) : 0u;
-        if (ov) b.closed_epoch[j] = b.call_epoch;
-        my_any |= ov;
-        my_open += live && b.closed_epoch[j] != b.call_epoch;
-        if (b.next_zero) b.next_zero[j] = 0;
+    for (uint32_t j0 = threadIdx.x; j0 < M; j0 += 4 * blockDim.x) {
+        uint32_t c[4], cp[4], ce[4];
+        uint8_t st[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const uint32_t j = j0 + e * blockDim.x;
+            if (j < M) { c[e] = from_local ? __ldcg(local + j) : b.glob[j]; cp[e] = b.cap[j]; ce[e] = b.closed_epoch[j]; st[e] = b.state[j]; }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const uint32_t j = j0 + e * blockDim.x;
+            if (j >= M) continue;
+            const bool live = st[e] & kNodeLive;
+            const bool ov = live && c[e] > cp[e];
+            if (from_local && local != b.glob) b.glob[j] = c[e];
+            b.over[j] = ov;
+            b.thr[j] = ov ? (uint32_t)((((unsigned long long)(c[e] - cp[e])) << 32) / c[e]) : 0u;
+            if (ov) b.closed_epoch[j] = b.call_epoch;
+            my_any |= ov;
+            my_open += live && !ov && ce[e] != b.call_epoch;
+            if (b.next_zero) b.next_zero[j] = 0;
+        }
     }
     if (my_any) atomicOr(&s_any, 1u);
     if (my_open) atomicAdd(&s_open, my_open);
     __syncthreads();
-    if (threadIdx.x == 0) {   // the sequence word goes last: the host polls it instead of paying a stream-synchronise wake-up
-        b.host_flags[0] = s_any; b.host_flags[1] = s_open;
-        __threadfence_system();
-        b.host_flags[2] = b.flag_seq;
+    if (threadIdx.x == 0) {
+        // ONE 16-byte store carries {any over, open nodes, sequence number}: it crosses PCIe as a single write, so the host, which
+        // polls the sequence word, never sees a torn report and the device needs no system-wide fence between the words
+        *reinterpret_cast<uint4 *>(const_cast<uint32_t *>(b.host_flags)) = make_uint4(s_any, s_open, b.flag_seq, 0u);
         __threadfence_system();
     }
 }

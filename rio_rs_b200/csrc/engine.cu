@@ -128,6 +128,23 @@ struct TabBufs {
 // device scalars (one small allocation): [0]=nsel [1]=moved/removed [2]=new keys (cumulative) [3]=placed ; u32 error at [8]
 enum { S_NSEL = 0, S_MOVED = 1, S_NEWKEYS = 2, S_PLACED = 3, S_FLAGS = 4 /* host-only: {any over, open nodes} written by k_exchange_check */, S_COUNT = 8 };
 
+// Device + host state of one bounded-load call in flight: capacities, global counters, thresholds, closed set,
+// the fused tail's ticket, and three words of mapped pinned memory the capacity check reports into.  Every resident set owns
+// one (so several sets can be between _begin and _end at once) and the handle owns one for the host-buffer call.
+struct BoundedState {
+    DevBuf buf;
+    uint32_t *h_flags = nullptr;              // pinned, mapped: {any over, open nodes, sequence number}
+    cudaEvent_t ev = nullptr;                 // "pass 0 done" for the check that runs on the auxiliary stream
+    uint32_t flag_seq = 0;                    // sequence number of the last check launched into h_flags
+    uint32_t epoch = 0;                       // closed-set tag of the current call
+    uint64_t cap_key[4] = {~0ull, 0, 0, 0};   // (n_total_objs, num << 32 | den, table version, M) the uploaded capacities belong to
+    // the call between _begin and _end
+    bool active = false;
+    uint64_t n_total_objs = 0;
+    uint32_t max_rounds = 0, M = 0;
+    void release(cudaStream_t st) { buf.release(st); if (h_flags) cudaFreeHost(h_flags); h_flags = nullptr; if (ev) cudaEventDestroy(ev); ev = nullptr; }
+};
+
 }  // namespace
 
 struct rio_placement {
@@ -135,7 +152,7 @@ struct rio_placement {
     int device = 0, sm_count = 0;
     size_t hbm = 0;
     std::string devname;
-    cudaStream_t stream = nullptr, h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaStream_t stream = nullptr, h2d_stream = nullptr, d2h_stream = nullptr, aux_stream = nullptr;   // aux: capacity checks of pipelined passes
     uint64_t launches = 0;
 
     std::vector<NodeInfo> nodes;
@@ -157,10 +174,7 @@ struct rio_placement {
 
     DevBuf s_keys, s_idx, s_idx2, s_sel, s_slots, s_keys2, s_feats, s_packed, s_offsets, s_cost, s_misc, s_flush, s_gather;
     // bounded-load state kept on the device between passes: [ticket | cap | global counters | thr | closed epoch | over] x node
-    DevBuf d_bounded;
-    uint32_t bounded_epoch = 0;               // closed-set tag of the current bounded call
-    uint32_t flag_seq = 0;                    // sequence number of the last capacity check launched
-    uint64_t cap_key[4] = {~0ull, 0, 0, 0};   // (n_total_objs, num << 32 | den, table version, M) the uploaded capacities belong to
+    BoundedState bs;                          // for rio_cuda_assign_bounded_batch (host buffers)
     uint64_t tab_version = 0;
     unsigned long long *d_scalars = nullptr;   // S_COUNT u64 + error u32
     unsigned long long *h_scalars = nullptr;   // pinned mirror
@@ -187,6 +201,7 @@ struct rio_objset {
     uint32_t K = 0;
     uint32_t counters_n = 0;
     bool alt_zero = false;     // counters_alt is known to be all zero (the capacity check of the last bounded pass cleared it)
+    BoundedState bs;
     bool assigned = false;
 };
 
@@ -517,17 +532,22 @@ void assign_host_pipelined(rio_placement *h, const uint64_t *keys, const float *
 // the default factor 1.25) do the thresholds get used by the spill selection and the closed set come back to the host for the
 // masked table of the next pass.
 struct BoundedDev { uint32_t *cap, *glob, *thr, *closed_epoch, *ticket; uint8_t *over; };
-BoundedDev bounded_layout(rio_placement *h, uint32_t M) {
+BoundedDev bounded_layout(rio_placement *h, BoundedState &bs, uint32_t M) {
     const size_t m = std::max(M, 1u);
     const size_t need = m * 17 + 64;
-    if (need > h->d_bounded.bytes) {
-        h->d_bounded.ensure(need, h->stream);
-        CUDA_TRY(cudaMemsetAsync(h->d_bounded.p, 0, h->d_bounded.bytes, h->stream));   // closed epochs and the ticket start at 0
-        h->bounded_epoch = 0;
-        h->cap_key[0] = ~0ull;
+    if (need > bs.buf.bytes) {
+        bs.buf.ensure(need, h->stream);
+        CUDA_TRY(cudaMemsetAsync(bs.buf.p, 0, bs.buf.bytes, h->stream));   // closed epochs and the ticket start at 0
+        bs.epoch = 0;
+        bs.cap_key[0] = ~0ull;
+    }
+    if (!bs.h_flags) {
+        CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&bs.h_flags), 16, cudaHostAllocMapped));
+        memset(bs.h_flags, 0, 16);
+        CUDA_TRY(cudaEventCreateWithFlags(&bs.ev, cudaEventDisableTiming));
     }
     BoundedDev b;
-    b.ticket = h->d_bounded.as<uint32_t>();          // 16 words reserved
+    b.ticket = bs.buf.as<uint32_t>();          // 16 words reserved
     b.cap = b.ticket + 16;
     b.glob = b.cap + m;
     b.thr = b.glob + m;
@@ -536,7 +556,7 @@ BoundedDev bounded_layout(rio_placement *h, uint32_t M) {
     return b;
 }
 
-BoundedTail make_tail(rio_placement *h, const BoundedDev &b, uint32_t M, uint32_t *next_zero, bool peer_exchange) {
+BoundedTail make_tail(rio_placement *h, BoundedState &bs, const BoundedDev &b, uint32_t M, uint32_t *next_zero, bool peer_exchange) {
     BoundedTail t{};
     t.enabled = 1;
     t.M = M;
@@ -547,12 +567,12 @@ BoundedTail make_tail(rio_placement *h, const BoundedDev &b, uint32_t M, uint32_
         for (int p = 0; p < h->world && p < 16; p++) t.peers.win[p] = h->xchg_peer[p];
         t.rank = (uint32_t)h->rank; t.world = (uint32_t)h->world; t.max_nodes = h->xchg_nodes; t.xchg_epoch = ++h->xchg_epoch;
     }
-    t.glob = b.glob; t.cap = b.cap; t.state = h->tabs.state; t.closed_epoch = b.closed_epoch; t.call_epoch = h->bounded_epoch;
+    t.glob = b.glob; t.cap = b.cap; t.state = h->tabs.state; t.closed_epoch = b.closed_epoch; t.call_epoch = bs.epoch;
     t.thr = b.thr; t.over = b.over;
     uint32_t *flags_dev = nullptr;
-    CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void **>(&flags_dev), h->h_scalars + S_FLAGS, 0));
+    CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void **>(&flags_dev), bs.h_flags, 0));
     t.host_flags = flags_dev;
-    t.flag_seq = ++h->flag_seq;
+    t.flag_seq = ++bs.flag_seq;
     return t;
 }
 
@@ -560,13 +580,13 @@ BoundedTail make_tail(rio_placement *h, const BoundedDev &b, uint32_t M, uint32_
 // write lands; a stream synchronise costs a driver wake-up (5-8 us) on top of a 60 us pass.  Everything the pass wrote to HBM is
 // ordered before the flag, later work on the stream is ordered behind the kernel as usual.  Falls back to a synchronise (which
 // also surfaces a failed kernel) if the number does not show up.
-std::pair<uint32_t, uint32_t> read_flags(rio_placement *h) {
-    const volatile uint32_t *flags = reinterpret_cast<const volatile uint32_t *>(h->h_scalars + S_FLAGS);
-    const auto t_end = std::chrono::steady_clock::now() + std::chrono::milliseconds(5);
-    while (flags[2] != h->flag_seq) {
+std::pair<uint32_t, uint32_t> read_flags(rio_placement *h, BoundedState &bs) {
+    const volatile uint32_t *flags = bs.h_flags;
+    const auto t_end = std::chrono::steady_clock::now() + std::chrono::milliseconds(20);
+    while (flags[2] != bs.flag_seq) {
         if (std::chrono::steady_clock::now() > t_end) {
             CUDA_TRY(cudaStreamSynchronize(h->stream));
-            REQUIRE(flags[2] == h->flag_seq, "capacity check did not report (internal error)");
+            REQUIRE(flags[2] == bs.flag_seq, "capacity check did not report (internal error)");
             break;
         }
 #if defined(__x86_64__)
@@ -577,55 +597,83 @@ std::pair<uint32_t, uint32_t> read_flags(rio_placement *h) {
     return {flags[0], flags[1]};
 }
 
-// one exchange + check as its own launch; returns {any over, open nodes}
-std::pair<uint32_t, uint32_t> exchange_and_check(rio_placement *h, const uint32_t *d_local, const BoundedDev &b, uint32_t M, uint32_t *next_zero) {
+// enqueue one exchange + check as its own launch (the result is picked up later with read_flags)
+void launch_check(rio_placement *h, BoundedState &bs, const uint32_t *d_local, const BoundedDev &b, uint32_t M, uint32_t *next_zero, cudaStream_t st) {
     const bool p2p = h->world > 1 && h->xchg_ready && M <= h->xchg_nodes;
     const uint32_t *src = d_local;
+    Launch L = h->L();
+    L.stream = st;
     if (!p2p && h->world > 1 && h->comm) {   // portable path: NCCL all-gather + sum, then the check alone
         h->s_gather.ensure((size_t)M * 4 * h->world, h->stream);
-        NCCL_TRY(g_nccl.AllGather(d_local, h->s_gather.p, M, kNcclUint32, h->comm, h->stream));
-        launch_sum_gathered(h->L(), h->s_gather.as<uint32_t>(), (uint32_t)h->world, M, b.glob);
+        if (st != h->stream) { CUDA_TRY(cudaEventRecord(h->ev_pipe[4], h->stream)); CUDA_TRY(cudaStreamWaitEvent(st, h->ev_pipe[4], 0)); }   // the gather buffer may just have been allocated
+        NCCL_TRY(g_nccl.AllGather(d_local, h->s_gather.p, M, kNcclUint32, h->comm, st));
+        launch_sum_gathered(L, h->s_gather.as<uint32_t>(), (uint32_t)h->world, M, b.glob);
         src = b.glob;
     }
-    launch_exchange_check(h->L(), src, make_tail(h, b, M, next_zero, p2p));
-    return read_flags(h);
+    launch_exchange_check(L, src, make_tail(h, bs, b, M, next_zero, p2p));
 }
 
-uint32_t bounded_rounds(rio_placement *h, const uint64_t *d_keys, uint64_t n, uint32_t *d_idx, uint32_t *d_counters, uint32_t *d_sel, uint32_t M,
-                        uint64_t n_total_objs, uint32_t cap_num, uint32_t cap_den, uint32_t max_rounds, bool first_pass_done, bool counters_zeroed,
-                        uint32_t *next_zero) {
+// First half of a bounded call: capacities, pass 0 and its check are enqueued; nothing is waited for (except the one-off
+// capacity upload when the table or the factor changed).
+// pipelined: the caller keeps several calls in flight (rio_cuda_set_assign_bounded_begin): the check then runs as its own one-CTA
+// kernel on the auxiliary stream behind an event, so the next set's walk starts the moment this one ends instead of waiting for the
+// ~8 us the last CTA needs for fence + ticket + check + the PCIe write.  One call at a time: the check rides in the walk kernel's
+// last CTA (one launch, lowest latency).
+void bounded_begin(rio_placement *h, BoundedState &bs, const uint64_t *d_keys, uint64_t n, uint32_t *d_idx, uint32_t *d_counters, uint32_t M,
+                   uint64_t n_total_objs, uint32_t cap_num, uint32_t cap_den, uint32_t max_rounds, bool first_pass_done, bool counters_zeroed, uint32_t *next_zero,
+                   bool pipelined = false) {
     cudaStream_t st = h->stream;
-    const BoundedDev b = bounded_layout(h, M);
+    REQUIRE(!bs.active, "a bounded call is already in flight on this set (call _end first)");
+    const BoundedDev b = bounded_layout(h, bs, M);
     const uint64_t key[4] = {n_total_objs, ((uint64_t)cap_num << 32) | cap_den, h->tab_version, M};
-    if (memcmp(key, h->cap_key, sizeof key) != 0) {   // capacities depend only on (N, factor, live weights): upload once per table
+    if (memcmp(key, bs.cap_key, sizeof key) != 0) {   // capacities depend only on (N, factor, live weights): upload once per table
         uint64_t W = 0;
         for (auto &ni : h->nodes) if (ni.live()) W += ni.weight;
         std::vector<uint32_t> cap(std::max(M, 1u), 0);
         for (uint32_t j = 0; j < M && j < h->nodes.size(); j++) if (h->nodes[j].live()) cap[j] = capacity_of(n_total_objs, h->nodes[j].weight, W, cap_num, cap_den);
         CUDA_TRY(cudaMemcpyAsync(b.cap, cap.data(), (size_t)std::max(M, 1u) * 4, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaStreamSynchronize(st));
-        memcpy(h->cap_key, key, sizeof key);
+        memcpy(bs.cap_key, key, sizeof key);
     }
-    if (++h->bounded_epoch == 0) {   // the closed set of a call is "closed_epoch[j] == this call's epoch": no memset per call
+    if (++bs.epoch == 0) {   // the closed set of a call is "closed_epoch[j] == this call's epoch": no memset per call
         CUDA_TRY(cudaMemsetAsync(b.closed_epoch, 0, (size_t)std::max(M, 1u) * 4, st));
-        h->bounded_epoch = 1;
+        bs.epoch = 1;
     }
     bool fused = false;
     if (!first_pass_done) {
         if (!counters_zeroed) CUDA_TRY(cudaMemsetAsync(d_counters, 0, (size_t)std::max(M, 1u) * 4, st));
         const bool p2p = h->world > 1 && h->xchg_ready && M <= h->xchg_nodes;
-        if (max_rounds > 1 && h->solver == RIO_SOLVER_HRW2 && (h->world == 1 || p2p)) {
-            const BoundedTail t = make_tail(h, b, M, next_zero, p2p);   // walk + histogram + exchange + check: ONE launch
+        if (!pipelined && max_rounds > 1 && h->solver == RIO_SOLVER_HRW2 && (h->world == 1 || p2p)) {
+            const BoundedTail t = make_tail(h, bs, b, M, next_zero, p2p);   // walk + histogram + exchange + check: ONE launch
             launch_assign_trie(h->L(), d_keys, n, h->tabs.trie, d_idx, d_counters, nullptr, 0, h->tabs.tab.n_total, &t);
             fused = true;
         } else {
             run_assign(h, h->solver, h->tabs, d_keys, n, d_idx, d_counters, nullptr, 0);
         }
     }
+    if (!fused && max_rounds > 1) {
+        if (pipelined) {
+            CUDA_TRY(cudaEventRecord(bs.ev, st));
+            CUDA_TRY(cudaStreamWaitEvent(h->aux_stream, bs.ev, 0));
+            launch_check(h, bs, d_counters, b, M, next_zero, h->aux_stream);
+        } else {
+            launch_check(h, bs, d_counters, b, M, next_zero, st);
+        }
+    }
+    bs.active = true;
+    bs.n_total_objs = n_total_objs; bs.max_rounds = max_rounds; bs.M = M;
+}
+
+// Second half: wait for the check (two words in mapped memory), run the spill rounds it asks for.  Returns the passes run.
+uint32_t bounded_end(rio_placement *h, BoundedState &bs, const uint64_t *d_keys, uint64_t n, uint32_t *d_idx, uint32_t *d_counters, uint32_t *d_sel) {
+    REQUIRE(bs.active, "no bounded call in flight on this set");
+    bs.active = false;
+    cudaStream_t st = h->stream;
+    const uint32_t M = bs.M;
+    const BoundedDev b = bounded_layout(h, bs, M);
     uint32_t passes = 1;
-    for (uint32_t r = 1; r < max_rounds; r++) {
-        const auto [any, open] = fused ? read_flags(h) : exchange_and_check(h, d_counters, b, M, next_zero);   // the one collective of this pass
-        fused = false;
+    for (uint32_t r = 1; r < bs.max_rounds; r++) {
+        const auto [any, open] = read_flags(h, bs);                  // the one collective of the pass has happened on the device
         if (!any || !open) break;
         zero_scalar(h, S_NSEL);
         launch_select_spill(h->L(), d_keys, d_idx, n, b.thr, b.over, r, d_sel, h->d_scalars + S_NSEL, d_counters);
@@ -633,10 +681,11 @@ uint32_t bounded_rounds(rio_placement *h, const uint64_t *d_keys, uint64_t n, ui
         CUDA_TRY(cudaMemcpyAsync(ce.data(), b.closed_epoch, (size_t)M * 4, cudaMemcpyDeviceToHost, st));
         const uint64_t nsel = read_scalar(h, S_NSEL);
         std::vector<uint8_t> closed(M, 0);
-        for (uint32_t j = 0; j < M; j++) closed[j] = ce[j] == h->bounded_epoch;
+        for (uint32_t j = 0; j < M; j++) closed[j] = ce[j] == bs.epoch;
         build_tab(h, h->tabs_masked, &closed);
         if (nsel) run_assign(h, h->solver, h->tabs_masked, d_keys, n, d_idx, d_counters, d_sel, nsel);
         passes++;
+        if (r + 1 < bs.max_rounds) launch_check(h, bs, d_counters, b, M, nullptr, st);
     }
     return passes;
 }
@@ -719,6 +768,7 @@ rio_status rio_cuda_create(const rio_config *cfg, rio_placement **out) {
         CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
         for (auto &ev : h->events) CUDA_TRY(cudaEventCreate(&ev));
         for (auto &ev : h->ev_pipe) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         // keep freed blocks in the pool: the scratch buffers are re-used every call
@@ -762,7 +812,8 @@ void rio_cuda_destroy(rio_placement *h) {
     }
     for (TabBufs *tb : {&h->tabs, &h->tabs_masked}) if (tb->stage) cudaFreeHost(tb->stage);
     DevBuf *bufs[] = {&h->tabs.dev, &h->tabs_masked.dev, &h->d_fnode, &h->d_fnode_c, &h->d_fnode_g, &h->d_nidx_map, &h->s_keys, &h->s_idx, &h->s_idx2, &h->s_sel, &h->s_slots, &h->s_keys2, &h->s_feats,
-                      &h->s_packed, &h->s_offsets, &h->s_cost, &h->s_misc, &h->s_flush, &h->s_gather, &h->d_bounded};
+                      &h->s_packed, &h->s_offsets, &h->s_cost, &h->s_misc, &h->s_flush, &h->s_gather};
+    h->bs.release(h->stream);
     for (DevBuf *b : bufs) b->release(h->stream);
     if (h->dir.slots) cudaFreeAsync(h->dir.slots, h->stream);
     cudaStreamSynchronize(h->stream);
@@ -773,6 +824,7 @@ void rio_cuda_destroy(rio_placement *h) {
     cudaStreamDestroy(h->stream);
     cudaStreamDestroy(h->h2d_stream);
     cudaStreamDestroy(h->d2h_stream);
+    if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
     delete h;
 }
 
@@ -1030,8 +1082,8 @@ rio_status rio_cuda_assign_bounded_batch(rio_placement *h, const uint64_t *keys,
         // pass 0: chunk-pipelined H2D / score+histogram / D2H; the exchange + capacity check runs behind the last chunk while its
         // indices are still crossing PCIe
         assign_host_pipelined(h, keys, nullptr, n, out_idx, d_cnt, false);
-        const uint32_t passes = bounded_rounds(h, h->s_keys.as<uint64_t>(), n, h->s_idx.as<uint32_t>(), d_cnt, h->s_sel.as<uint32_t>(), M, n_total_objs, cap_num, cap_den,
-                                               max_rounds, true, true, nullptr);
+        bounded_begin(h, h->bs, h->s_keys.as<uint64_t>(), n, h->s_idx.as<uint32_t>(), d_cnt, M, n_total_objs, cap_num, cap_den, max_rounds, true, true, nullptr);
+        const uint32_t passes = bounded_end(h, h->bs, h->s_keys.as<uint64_t>(), n, h->s_idx.as<uint32_t>(), d_cnt, h->s_sel.as<uint32_t>());
         CUDA_TRY(cudaStreamSynchronize(h->d2h_stream));
         if (passes > 1) {   // a spill round rewrote some indices after their chunk had left: send the final state again
             CUDA_TRY(cudaMemcpyAsync(out_idx, h->s_idx.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -1216,7 +1268,7 @@ void rio_cuda_set_destroy(rio_objset *s) {
     {
         std::lock_guard<std::mutex> g(h->mu);
         cudaSetDevice(h->device);
-        s->keys.release(h->stream); s->idx.release(h->stream); s->feats.release(h->stream); s->counters.release(h->stream); s->counters_alt.release(h->stream); s->sel.release(h->stream);
+        s->keys.release(h->stream); s->idx.release(h->stream); s->feats.release(h->stream); s->counters.release(h->stream); s->counters_alt.release(h->stream); s->sel.release(h->stream); s->bs.release(h->stream);
         cudaStreamSynchronize(h->stream);
     }
     delete s;
@@ -1272,23 +1324,46 @@ rio_status rio_cuda_set_assign(rio_objset *s, uint32_t use_affinity) {
     });
 }
 
+static void set_bounded_begin(rio_objset *s, uint64_t n_total_objs, uint32_t cap_num, uint32_t cap_den, uint32_t max_rounds, bool pipelined) {
+    rio_placement *h = s->h;
+    REQUIRE(cap_den > 0 && max_rounds > 0, "bad capacity factor / rounds");
+    ensure_tab(h);
+    set_ensure_counters(s);
+    if (!n_total_objs) n_total_objs = s->n * (uint64_t)h->world;
+    // two counter buffers take turns: the check of this pass clears the other one, so the next pass starts without a memset
+    const bool zeroed = s->alt_zero;
+    if (zeroed) std::swap(s->counters, s->counters_alt);
+    bounded_begin(h, s->bs, s->keys.as<uint64_t>(), s->n, s->idx.as<uint32_t>(), s->counters.as<uint32_t>(), s->counters_n, n_total_objs, cap_num, cap_den, max_rounds,
+                  false, zeroed, s->counters_alt.as<uint32_t>(), pipelined);
+    s->alt_zero = max_rounds > 1;
+}
+static uint32_t set_bounded_end(rio_objset *s) {
+    rio_placement *h = s->h;
+    const uint32_t passes = bounded_end(h, s->bs, s->keys.as<uint64_t>(), s->n, s->idx.as<uint32_t>(), s->counters.as<uint32_t>(), s->sel.as<uint32_t>());
+    s->assigned = true;
+    if (s->bs.max_rounds == 1) CUDA_TRY(cudaStreamSynchronize(h->stream));   // otherwise the check's report already ordered the pass before this return
+    return passes;
+}
+
 rio_status rio_cuda_set_assign_bounded(rio_objset *s, uint64_t n_total_objs, uint32_t cap_num, uint32_t cap_den, uint32_t max_rounds, uint32_t *out_passes) {
     if (!s) { g_last_error = "null set"; return RIO_ERR_UNKNOWN; }
-    rio_placement *h = s->h;
-    return guarded(h, [&] {
-        REQUIRE(cap_den > 0 && max_rounds > 0, "bad capacity factor / rounds");
-        ensure_tab(h);
-        set_ensure_counters(s);
-        if (!n_total_objs) n_total_objs = s->n * (uint64_t)h->world;
-        // two counter buffers take turns: the check of this pass clears the other one, so the next pass starts without a memset
-        const bool zeroed = s->alt_zero;
-        if (zeroed) std::swap(s->counters, s->counters_alt);
-        const uint32_t passes = bounded_rounds(h, s->keys.as<uint64_t>(), s->n, s->idx.as<uint32_t>(), s->counters.as<uint32_t>(), s->sel.as<uint32_t>(), s->counters_n,
-                                               n_total_objs, cap_num, cap_den, max_rounds, false, zeroed, s->counters_alt.as<uint32_t>());
-        s->alt_zero = max_rounds > 1;
-        s->assigned = true;
+    return guarded(s->h, [&] {
+        set_bounded_begin(s, n_total_objs, cap_num, cap_den, max_rounds, false);
+        const uint32_t passes = set_bounded_end(s);
         if (out_passes) *out_passes = passes;
-        if (max_rounds == 1) CUDA_TRY(cudaStreamSynchronize(h->stream));   // otherwise the check's report already ordered the pass before this return
+    });
+}
+
+rio_status rio_cuda_set_assign_bounded_begin(rio_objset *s, uint64_t n_total_objs, uint32_t cap_num, uint32_t cap_den, uint32_t max_rounds) {
+    if (!s) { g_last_error = "null set"; return RIO_ERR_UNKNOWN; }
+    return guarded(s->h, [&] { set_bounded_begin(s, n_total_objs, cap_num, cap_den, max_rounds, true); });
+}
+
+rio_status rio_cuda_set_assign_bounded_end(rio_objset *s, uint32_t *out_passes) {
+    if (!s) { g_last_error = "null set"; return RIO_ERR_UNKNOWN; }
+    return guarded(s->h, [&] {
+        const uint32_t passes = set_bounded_end(s);
+        if (out_passes) *out_passes = passes;
     });
 }
 

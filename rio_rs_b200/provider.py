@@ -461,6 +461,14 @@ class ObjectSet:
         self._ck(self.L.rio_cuda_set_assign_bounded(self.s, n_total, cap_num, cap_den, max_rounds, C.byref(passes)))
         return passes.value
 
+    def assign_bounded_begin(self, n_total=0, cap_num=5, cap_den=4, max_rounds=4):
+        self._ck(self.L.rio_cuda_set_assign_bounded_begin(self.s, n_total, cap_num, cap_den, max_rounds))
+
+    def assign_bounded_end(self):
+        passes = C.c_uint32(0)
+        self._ck(self.L.rio_cuda_set_assign_bounded_end(self.s, C.byref(passes)))
+        return passes.value
+
     def rebalance(self, event, idx):
         m = C.c_uint64(0)
         self._ck(self.L.rio_cuda_set_rebalance(self.s, N.EV_JOIN if event == "join" else N.EV_LEAVE, idx, C.byref(m)))

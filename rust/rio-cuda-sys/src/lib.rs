@@ -80,6 +80,8 @@ extern "C" {
     pub fn rio_cuda_set_load_feats(s: *mut rio_objset, feats: *const f32, k: u32) -> rio_status;
     pub fn rio_cuda_set_assign(s: *mut rio_objset, use_affinity: u32) -> rio_status;
     pub fn rio_cuda_set_assign_bounded(s: *mut rio_objset, n_total: u64, cap_num: u32, cap_den: u32, max_rounds: u32, out_passes: *mut u32) -> rio_status;
+    pub fn rio_cuda_set_assign_bounded_begin(s: *mut rio_objset, n_total: u64, cap_num: u32, cap_den: u32, max_rounds: u32) -> rio_status;
+    pub fn rio_cuda_set_assign_bounded_end(s: *mut rio_objset, out_passes: *mut u32) -> rio_status;
     pub fn rio_cuda_set_rebalance(s: *mut rio_objset, event: u32, idx: u32, out_moved: *mut u64) -> rio_status;
     pub fn rio_cuda_set_counters(s: *mut rio_objset, out: *mut u32, cap: u32) -> rio_status;
     pub fn rio_cuda_set_read(s: *mut rio_objset, first: u64, n: u64, out_keys: *mut u64, out_idx: *mut u32) -> rio_status;

@@ -246,3 +246,34 @@ def test_client_first_hop_reaches_the_owner_without_redirect(gp, oracle):
     w2[9] = 0
     fh.set_active_servers(addrs, w2)
     assert (fh.first_hop_batch(keys) == p.lookup_many(keys)).all()
+
+
+def test_bounded_calls_in_flight_on_several_sets(gp, oracle):
+    """rio_cuda_set_assign_bounded_begin / _end: three resident sets have their pass 0 (walk + histogram + capacity check, one
+    kernel each) queued back to back before any check is read; one of them needs spill rounds.  Each must end exactly like the
+    one-call form and like the oracle, whatever order the _end calls come in."""
+    p = provider(gp)
+    addrs, seeds, w = oracle.synth_nodes(64)
+    p.set_nodes(addrs, w)
+    n = 150_000
+    sets, keys = [], []
+    for k in range(3):
+        s = p.new_set(n)
+        s.synth_keys(k * n, n, 5)
+        sets.append(s)
+        keys.append(oracle.synth_keys(n, 5, first=k * n))
+    caps = [(5, 4), (101, 100), (1, 1)]
+    for rep in range(3):   # repeated: the two counter buffers of each set take turns, the closed-set epochs advance
+        for s, cap in zip(sets, caps):
+            s.assign_bounded_begin(0, cap[0], cap[1], 4)
+        for k in (2, 0, 1):
+            passes = sets[k].assign_bounded_end()
+            widx, wcnt, wpass = oracle.assign_bounded_hrw2(keys[k], seeds, w, caps[k][0], caps[k][1], 4, threads=8)
+            assert passes == wpass, (rep, k)
+            assert (sets[k].read() == widx).all() and (sets[k].counters() == wcnt).all(), (rep, k)
+    with pytest.raises(gp.Unknown):
+        sets[0].assign_bounded_end()               # nothing in flight
+    sets[0].assign_bounded_begin(0, 5, 4, 4)
+    with pytest.raises(gp.Unknown):
+        sets[0].assign_bounded_begin(0, 5, 4, 4)   # one bounded call per set at a time
+    assert sets[0].assign_bounded_end() >= 1

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, n, M, q, comm):
+def _worker(rank, world, port, n, M, q, comm, solver):
     sys.path.insert(0, ROOT)
     os.environ["RIO_COMM"] = comm   # "p2p": CUDA-IPC windows over NVLink (default), "nccl": ncclAllGather
     import torch.distributed as dist
@@ -25,11 +25,12 @@ def _worker(rank, world, port, n, M, q, comm):
     parallel.init_comm(p, dist)
     addrs, seeds, w = O.synth_nodes(M)
     p.set_nodes(addrs, w)
+    p.set_solver(solver)
     lo, hi = parallel.shard_range(n, rank, world)
     s = p.new_set(hi - lo)
     s.synth_keys(lo, hi - lo, 1)
     out = {}
-    for cap in [(5, 4), (101, 100)]:
+    for cap in [(5, 4), (101, 100), (5, 4), (1, 1)]:   # repeated factors: the two counter buffers of a set take turns across calls
         passes = s.assign_bounded(n, cap[0], cap[1], 4)
         out[cap] = (passes, s.read().tolist(), s.counters().tolist())
     # plain assignment + a leave and a join, counters are global after the exchange
@@ -46,8 +47,11 @@ def _worker(rank, world, port, n, M, q, comm):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("solver", ["hrw", "hrw2"])
 @pytest.mark.parametrize("comm", ["p2p", "nccl"])
-def test_two_gpu_sharded_results_equal_single_process_oracle(oracle, comm):
+def test_two_gpu_sharded_results_equal_single_process_oracle(oracle, comm, solver):
+    """Both exchange paths x both solver policies.  Under hrw2 + p2p the whole pass (walk, histogram, exchange over NVLink peer
+    memory, capacity check) is ONE kernel per rank, the last CTA of each rank's walk spinning on its peers' flags."""
     import torch
     import torch.multiprocessing as mp
 
@@ -59,8 +63,8 @@ def test_two_gpu_sharded_results_equal_single_process_oracle(oracle, comm):
     n, M, world = 400_000, 48, 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + os.getpid() % 1000 + (7 if comm == "nccl" else 0)
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, M, q, comm)) for r in range(world)]
+    port = 29600 + os.getpid() % 1000 + (7 if comm == "nccl" else 0) + (13 if solver == "hrw2" else 0)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, M, q, comm, solver)) for r in range(world)]
     for pr in procs:
         pr.start()
     res = sorted(q.get(timeout=600) for _ in range(world))
@@ -69,18 +73,21 @@ def test_two_gpu_sharded_results_equal_single_process_oracle(oracle, comm):
         assert pr.exitcode == 0
     _, seeds, w = oracle.synth_nodes(M)
     keys = oracle.synth_keys(n, 1)
-    for cap in [(5, 4), (101, 100)]:
-        widx, wcnt, wpass = oracle.assign_bounded(keys, seeds, w, cap[0], cap[1], 4, threads=8)
+    def assign(weights):
+        return oracle.assign_hrw2(keys, seeds, weights, threads=8) if solver == "hrw2" else oracle.assign_hrw(keys, seeds, weights, threads=8)
+
+    for cap in [(5, 4), (101, 100), (1, 1)]:
+        widx, wcnt, wpass = (oracle.assign_bounded_hrw2 if solver == "hrw2" else oracle.assign_bounded)(keys, seeds, w, cap[0], cap[1], 4, threads=8)
         got = np.empty(n, dtype=np.uint32)
         for rank, lo, hi, out, *_ in res:
             passes, idx, cnt = out[cap]
             got[lo:hi] = idx
             assert passes == wpass and cnt == wcnt.tolist()   # counters are the GLOBAL ones on every rank
         assert (got == widx).all(), cap
-    base = oracle.assign_hrw(keys, seeds, w, threads=8)
+    base = assign(w)
     w2 = w.copy()
     w2[5] = 0
-    left = oracle.assign_hrw(keys, seeds, w2, threads=8)
+    left = assign(w2)
     got_l, got_j = np.empty(n, dtype=np.uint32), np.empty(n, dtype=np.uint32)
     ml = mj = 0
     for rank, lo, hi, _, moved_leave, after_leave, moved_join, after_join, summed in res:
