@@ -96,6 +96,8 @@ rio_status  rio_cuda_node_index(rio_placement *h, const char *address, uint32_t 
 rio_status  rio_cuda_node_intern(rio_placement *h, const char *address, uint32_t *out_idx);
 rio_status  rio_cuda_node_address(rio_placement *h, uint32_t idx, char *buf, size_t cap, size_t *out_len);
 rio_status  rio_cuda_node_count(rio_placement *h, uint32_t *out_total, uint32_t *out_live);
+/* membership flag, weight and "address has no ip:port shape" (service.rs:213-222) of an interned node; any out may be NULL */
+rio_status  rio_cuda_node_state(rio_placement *h, uint32_t idx, int32_t *active, uint32_t *weight, int32_t *malformed);
 
 /* ---- solver policy of the handle (new; no reference counterpart) ----------------------------------------------------
  * RIO_SOLVER_HRW  = flat weighted rendezvous over all live nodes: M pair hashes per object, minimal movement
@@ -255,6 +257,31 @@ rio_status  rio_cuda_resolver_update_str(rio_resolver *r, const char *type, size
                                          const char *address, size_t address_len);
 rio_status  rio_cuda_resolver_stats(rio_resolver *r, uint64_t *calls, uint64_t *batches, uint64_t *largest_batch);
 const char *rio_cuda_resolver_last_error(void);
+
+/* ---- durable write-through into the reference's SQLite schema -------------------------------------------
+ * SqliteObjectPlacement (sqlite.rs:58-126) in front of which the GPU directory sits as the cache: the table
+ * `object_placement(struct_name, object_id, server_address)` of migrations/0001-sqlite-init.sql:1-9 is the source of truth across
+ * restarts, every call below executes the reference's own SQL text and the matching GPU mutation; lookups are answered by the
+ * GPU directory.  libsqlite3.so.0 is dlopen'ed on first use.  Errors: RIO_ERR_UPSTREAM (SQLite / CUDA) like the reference's
+ * From<sqlx::Error> (errors.rs:145-152); message in rio_cuda_durable_last_error() (thread-local). */
+typedef struct rio_durable rio_durable;
+rio_status  rio_cuda_durable_open(rio_placement *h, const char *path, rio_durable **out);      /* prepare(): migration in one transaction */
+void        rio_cuda_durable_close(rio_durable *d);
+rio_status  rio_cuda_durable_recover(rio_durable *d, uint64_t *out_rows);                      /* table -> GPU directory, in bulk */
+rio_status  rio_cuda_durable_update(rio_durable *d, const char *type, size_t type_len, const char *id, size_t id_len,
+                                    const char *address, size_t address_len);                  /* address NULL = update(None) = remove */
+rio_status  rio_cuda_durable_lookup(rio_durable *d, const char *type, size_t type_len, const char *id, size_t id_len,
+                                    char *buf, size_t cap, size_t *out_len);
+rio_status  rio_cuda_durable_clean_server(rio_durable *d, const char *address, size_t address_len);
+rio_status  rio_cuda_durable_remove(rio_durable *d, const char *type, size_t type_len, const char *id, size_t id_len);
+/* n NUL-terminated (type, id, address-or-NULL) triples: ONE transaction on the table + one batched upsert on the GPU */
+rio_status  rio_cuda_durable_update_batch(rio_durable *d, const char *const *types, const char *const *ids,
+                                          const char *const *addresses, size_t n);
+/* get_or_create_placement for n ids (service.rs:193-254) decided on the GPU, then written through in ONE transaction: rows of the
+ * inactive servers the batch met are deleted (clean_server), changed placements upserted */
+rio_status  rio_cuda_durable_place_batch(rio_durable *d, const char *const *types, const char *const *ids, size_t n,
+                                         uint32_t policy, uint32_t self_idx, uint32_t *out_idx);
+const char *rio_cuda_durable_last_error(void);
 
 #ifdef __cplusplus
 }

@@ -49,6 +49,7 @@ SIGNATURES = {
     "rio_cuda_node_intern": (C.c_int32, [H, C.c_char_p, u32p]),
     "rio_cuda_node_address": (C.c_int32, [H, C.c_uint32, C.c_char_p, sz, C.POINTER(sz)]),
     "rio_cuda_node_count": (C.c_int32, [H, u32p, u32p]),
+    "rio_cuda_node_state": (C.c_int32, [H, C.c_uint32, C.POINTER(C.c_int32), u32p, C.POINTER(C.c_int32)]),
     "rio_cuda_set_solver": (C.c_int32, [H, C.c_uint32, C.c_uint32]),
     "rio_cuda_get_solver": (C.c_int32, [H, u32p, u32p]),
     "rio_cuda_lookup_batch": (C.c_int32, [H, vp, sz, vp]),
@@ -101,6 +102,16 @@ SIGNATURES = {
     "rio_cuda_resolver_update_str": (C.c_int32, [H, C.c_char_p, sz, C.c_char_p, sz, C.c_char_p, sz]),
     "rio_cuda_resolver_stats": (C.c_int32, [H, u64p, u64p, u64p]),
     "rio_cuda_resolver_last_error": (C.c_char_p, []),
+    "rio_cuda_durable_open": (C.c_int32, [H, C.c_char_p, C.POINTER(H)]),
+    "rio_cuda_durable_close": (None, [H]),
+    "rio_cuda_durable_recover": (C.c_int32, [H, u64p]),
+    "rio_cuda_durable_update": (C.c_int32, [H, C.c_char_p, sz, C.c_char_p, sz, C.c_char_p, sz]),
+    "rio_cuda_durable_lookup": (C.c_int32, [H, C.c_char_p, sz, C.c_char_p, sz, C.c_char_p, sz, C.POINTER(sz)]),
+    "rio_cuda_durable_clean_server": (C.c_int32, [H, C.c_char_p, sz]),
+    "rio_cuda_durable_remove": (C.c_int32, [H, C.c_char_p, sz, C.c_char_p, sz]),
+    "rio_cuda_durable_update_batch": (C.c_int32, [H, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), sz]),
+    "rio_cuda_durable_place_batch": (C.c_int32, [H, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), sz, C.c_uint32, C.c_uint32, vp]),
+    "rio_cuda_durable_last_error": (C.c_char_p, []),
     "rio_cuda_update_str": (C.c_int32, [H, C.c_char_p, sz, C.c_char_p, sz, C.c_char_p, sz]),
     "rio_cuda_lookup_str": (C.c_int32, [H, C.c_char_p, sz, C.c_char_p, sz, C.c_char_p, sz, C.POINTER(sz)]),
     "rio_cuda_clean_server_str": (C.c_int32, [H, C.c_char_p, sz]),

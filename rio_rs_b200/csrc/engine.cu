@@ -950,6 +950,16 @@ rio_status rio_cuda_node_count(rio_placement *h, uint32_t *out_total, uint32_t *
     });
 }
 
+rio_status rio_cuda_node_state(rio_placement *h, uint32_t idx, int32_t *active, uint32_t *weight, int32_t *malformed) {
+    if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
+    return guarded(h, [&] {
+        REQUIRE(idx < h->nodes.size(), "node index out of range");
+        if (active) *active = h->nodes[idx].active ? 1 : 0;
+        if (weight) *weight = h->nodes[idx].weight;
+        if (malformed) *malformed = h->nodes[idx].malformed ? 1 : 0;
+    });
+}
+
 rio_status rio_cuda_set_solver(rio_placement *h, uint32_t solver, uint32_t trie_bits) {
     if (!h) { g_last_error = "null handle"; return RIO_ERR_UNKNOWN; }
     return guarded(h, [&] {

@@ -25,6 +25,8 @@ pub struct rio_objset {
     _private: [u8; 0],
 }
 #[repr(C)]
+pub struct rio_durable { _private: [u8; 0] }
+#[repr(C)]
 pub struct rio_resolver {
     _private: [u8; 0],
 }
@@ -59,6 +61,7 @@ extern "C" {
     pub fn rio_cuda_node_count(h: *mut rio_placement, out_total: *mut u32, out_live: *mut u32) -> rio_status;
     pub fn rio_cuda_assign_bounded_batch(h: *mut rio_placement, keys: *const u64, n: usize, n_total: u64, cap_num: u32, cap_den: u32, max_rounds: u32, out_idx: *mut u32, out_passes: *mut u32) -> rio_status;
     pub fn rio_cuda_check_address_batch(h: *mut rio_placement, addr_idx: *const u32, n: usize, self_idx: u32, out_verdict: *mut u8, out_cleaned: *mut u64) -> rio_status;
+    pub fn rio_cuda_node_state(h: *mut rio_placement, idx: u32, active: *mut i32, weight: *mut u32, malformed: *mut i32) -> rio_status;
     pub fn rio_cuda_set_solver(h: *mut rio_placement, solver: u32, trie_bits: u32) -> rio_status;
     pub fn rio_cuda_get_solver(h: *mut rio_placement, solver: *mut u32, trie_bits: *mut u32) -> rio_status;
 
@@ -116,6 +119,16 @@ extern "C" {
     pub fn rio_cuda_resolver_stats(r: *mut rio_resolver, calls: *mut u64, batches: *mut u64, largest_batch: *mut u64) -> rio_status;
     pub fn rio_cuda_resolver_last_error() -> *const c_char;
 
+    pub fn rio_cuda_durable_open(h: *mut rio_placement, path: *const c_char, out: *mut *mut rio_durable) -> rio_status;
+    pub fn rio_cuda_durable_close(d: *mut rio_durable);
+    pub fn rio_cuda_durable_recover(d: *mut rio_durable, out_rows: *mut u64) -> rio_status;
+    pub fn rio_cuda_durable_update(d: *mut rio_durable, ty: *const c_char, ty_len: usize, id: *const c_char, id_len: usize, address: *const c_char, address_len: usize) -> rio_status;
+    pub fn rio_cuda_durable_lookup(d: *mut rio_durable, ty: *const c_char, ty_len: usize, id: *const c_char, id_len: usize, buf: *mut c_char, cap: usize, out_len: *mut usize) -> rio_status;
+    pub fn rio_cuda_durable_clean_server(d: *mut rio_durable, address: *const c_char, address_len: usize) -> rio_status;
+    pub fn rio_cuda_durable_remove(d: *mut rio_durable, ty: *const c_char, ty_len: usize, id: *const c_char, id_len: usize) -> rio_status;
+    pub fn rio_cuda_durable_update_batch(d: *mut rio_durable, types: *const *const c_char, ids: *const *const c_char, addresses: *const *const c_char, n: usize) -> rio_status;
+    pub fn rio_cuda_durable_place_batch(d: *mut rio_durable, types: *const *const c_char, ids: *const *const c_char, n: usize, policy: u32, self_idx: u32, out_idx: *mut u32) -> rio_status;
+    pub fn rio_cuda_durable_last_error() -> *const c_char;
     pub fn rio_cuda_update_str(h: *mut rio_placement, ty: *const c_char, ty_len: size_t, id: *const c_char, id_len: size_t, address: *const c_char, address_len: size_t) -> rio_status;
     pub fn rio_cuda_lookup_str(h: *mut rio_placement, ty: *const c_char, ty_len: size_t, id: *const c_char, id_len: size_t, buf: *mut c_char, cap: size_t, out_len: *mut size_t) -> rio_status;
     pub fn rio_cuda_clean_server_str(h: *mut rio_placement, address: *const c_char, address_len: size_t) -> rio_status;

@@ -434,7 +434,7 @@ def test_place_batch_hrw_policy(gp, oracle):
     assert (rest[want[10000:] == 5] == NONE).all() and (rest[want[10000:] != 5] == want[10000:][want[10000:] != 5]).all()
 
 
-# ---- full-size properties (BASELINE sizes; the oracle checks a sample) -------------------------------------------------
+# ---- full-size properties (BASELINE sizes; every object is checked against the oracle) -------------------------------------------------
 def test_full_size_10m_x_1024_properties(gp, oracle):
     n, M = 10_000_000, 1024
     p = provider(gp)
@@ -446,11 +446,9 @@ def test_full_size_10m_x_1024_properties(gp, oracle):
     idx = s.read()
     cnt = s.counters()
     assert cnt.sum() == n and (cnt == np.bincount(idx, minlength=M)).all()
-    # sample of 50k objects against the oracle
-    rng = np.random.default_rng(1)
-    pick = np.sort(rng.choice(n, 50000, replace=False))
+    # EVERY object against the oracle (10 M x 1024 pair hashes each on all host cores: a few seconds on the GPU box)
     keys = oracle.synth_keys(n, 1)
-    assert (idx[pick] == oracle.assign_hrw(keys[pick], seeds, w, threads=8)).all()
+    assert (idx == oracle.assign_hrw(keys, seeds, w, threads=os.cpu_count() or 8)).all()
     # weights respected: chi-square of counts against w/W
     e = n * w / w.sum()
     chi = ((cnt - e) ** 2 / e).sum()
