@@ -321,6 +321,7 @@ void build_tab(rio_placement *h, TabBufs &tb, const std::vector<uint8_t> *closed
                  total = al(o_live + livef.size() * 4);
     cudaStream_t st = h->stream;
     if (tb.upload_pending) { CUDA_TRY(cudaStreamSynchronize(st)); tb.upload_pending = false; }   // the previous copy still reads the staging area
+    if (h->aux_stream) CUDA_TRY(cudaStreamSynchronize(h->aux_stream));   // a pipelined capacity check may still be reading the old table's node states
     if (total > tb.stage_cap) {
         if (tb.stage) CUDA_TRY(cudaFreeHost(tb.stage));
         tb.stage = nullptr; tb.stage_cap = 0;
@@ -497,8 +498,10 @@ void assign_host_pipelined(rio_placement *h, const uint64_t *keys, const float *
     if (feats) REQUIRE(h->K > 0, "assign with object features needs node features (set_nodes feats)");
     // chunks of two full kernel waves (about 0.9 M objects on 148 SMs): whole waves leave no tail, small chunks keep the
     // pipeline fill/drain (first H2D, last D2H) short
+    // HRW2 walks a chunk in microseconds, so PCIe is the only clock: small chunks (512 Ki objects = 4 MiB in, 2 MiB out) keep the
+    // pipeline's fill (first H2D) and drain (last D2H) at ~0.1 ms of an 80 MB transfer
     const size_t chunk = feats ? (size_t)(1u << 20)
-                               : (h->solver == RIO_SOLVER_HRW2 ? (size_t)(4 * trie_wave_objects(h->sm_count)) : (size_t)(2 * assign_wave_objects(h->sm_count)));
+                               : (h->solver == RIO_SOLVER_HRW2 ? (size_t)(1u << 19) : (size_t)(2 * assign_wave_objects(h->sm_count)));
     if (!feats) h->s_keys.ensure(n * 8, h->stream);
     h->s_idx.ensure(n * 4, h->stream);
     if (feats) h->s_feats.ensure(n * (size_t)h->K * 4, h->stream);
@@ -768,7 +771,11 @@ rio_status rio_cuda_create(const rio_config *cfg, rio_placement **out) {
         CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+        {   // highest priority: its one-CTA kernels must not queue behind the next set's walk
+            int lo_prio = 0, hi_prio = 0;
+            CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+            CUDA_TRY(cudaStreamCreateWithPriority(&h->aux_stream, cudaStreamNonBlocking, hi_prio));
+        }
         for (auto &ev : h->events) CUDA_TRY(cudaEventCreate(&ev));
         for (auto &ev : h->ev_pipe) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         // keep freed blocks in the pool: the scratch buffers are re-used every call
@@ -804,6 +811,7 @@ void rio_cuda_destroy(rio_placement *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    if (h->aux_stream) cudaStreamSynchronize(h->aux_stream);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     if (h->xchg_mine) {
         for (int p = 0; p < h->world && p < 16; p++)
@@ -1278,6 +1286,7 @@ void rio_cuda_set_destroy(rio_objset *s) {
     {
         std::lock_guard<std::mutex> g(h->mu);
         cudaSetDevice(h->device);
+        if (h->aux_stream) cudaStreamSynchronize(h->aux_stream);   // a check of this set may still be in flight
         s->keys.release(h->stream); s->idx.release(h->stream); s->feats.release(h->stream); s->counters.release(h->stream); s->counters_alt.release(h->stream); s->sel.release(h->stream); s->bs.release(h->stream);
         cudaStreamSynchronize(h->stream);
     }

@@ -425,21 +425,25 @@ bool launch_assign_affinity_umma(const Launch &L, const float *d_fobj, uint64_t 
     UmmaParams P{d_fobj, n, d_fnode_c, d_nidx_map, n_live, m_pad, d_out_idx, d_out_cost, d_counters, kRows * 16u, 128u, m_pad * 16u, 128u, g_umma_timing};
     const uint64_t n_rb = (n + kRows - 1) / kRows;
     const int grid = (int)(n_rb < (uint64_t)L.sm_count ? n_rb : (uint64_t)L.sm_count);
-    const char *e = getenv("RIO_UMMA_LDW");   // x32 TMEM loads per double-buffer stage (A/B runs): 1 or 2 (default)
-    const int ldw = e ? atoi(e) : 2;
+    cudaError_t attr = cudaSuccess;
     if (small) {
-        cudaFuncSetAttribute(k_affinity_umma<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_affinity_umma<64, 1><<<grid, kUmmaThreads, smem, L.stream>>>(P);
-    } else if (ldw == 1) {
-        cudaFuncSetAttribute(k_affinity_umma<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_affinity_umma<256, 1><<<grid, kUmmaThreads, smem, L.stream>>>(P);
-    } else if (getenv("RIO_UMMA_NT") && atoi(getenv("RIO_UMMA_NT")) == 128) {   // A/B: four 128-column accumulators
-        cudaFuncSetAttribute(k_affinity_umma<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_affinity_umma<128, 2><<<grid, kUmmaThreads, smem, L.stream>>>(P);
+        attr = cudaFuncSetAttribute(k_affinity_umma<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (attr == cudaSuccess) k_affinity_umma<64, 1><<<grid, kUmmaThreads, smem, L.stream>>>(P);
+#ifdef RIO_ASSIGN_TUNING   // A/B points of the epilogue (RIO_BUILD_TUNING=1): not in the shipped library
+    } else if (getenv("RIO_UMMA_LDW") && atoi(getenv("RIO_UMMA_LDW")) == 1) {   // one x32 TMEM load per double-buffer stage
+        attr = cudaFuncSetAttribute(k_affinity_umma<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (attr == cudaSuccess) k_affinity_umma<256, 1><<<grid, kUmmaThreads, smem, L.stream>>>(P);
+    } else if (getenv("RIO_UMMA_NT") && atoi(getenv("RIO_UMMA_NT")) == 128) {   // four 128-column accumulators
+        attr = cudaFuncSetAttribute(k_affinity_umma<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (attr == cudaSuccess) k_affinity_umma<128, 2><<<grid, kUmmaThreads, smem, L.stream>>>(P);
+#endif
     } else {
-        cudaFuncSetAttribute(k_affinity_umma<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_affinity_umma<256, 2><<<grid, kUmmaThreads, smem, L.stream>>>(P);
+        attr = cudaFuncSetAttribute(k_affinity_umma<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (attr == cudaSuccess) k_affinity_umma<256, 2><<<grid, kUmmaThreads, smem, L.stream>>>(P);
     }
+    // a launch that did not happen (shared memory over the limit, a device without tcgen05) must not leave the caller with stale
+    // indices: report it, the engine then runs the CUDA-core kernel instead
+    if (attr != cudaSuccess || cudaPeekAtLastError() != cudaSuccess) { cudaGetLastError(); return false; }
     RIO_COUNT_LAUNCH(L);
     {
         const uint32_t bins = (d_counters && n_total <= 8192) ? n_total : 0;

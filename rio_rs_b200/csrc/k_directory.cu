@@ -327,10 +327,14 @@ k_select_on_node(const uint32_t *__restrict__ idx, uint64_t n, uint32_t node, ui
             else if (v < n4) { x[e].x = __ldg(idx + 4 * v); x[e].y = 4 * v + 1 < n ? __ldg(idx + 4 * v + 1) : ~node; x[e].z = 4 * v + 2 < n ? __ldg(idx + 4 * v + 2) : ~node; x[e].w = ~node; }
             else x[e] = make_uint4(~node, ~node, ~node, ~node);
         }
+        uint32_t hits4[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) hits4[e] = (x[e].x == node) | ((x[e].y == node) << 1) | ((x[e].z == node) << 2) | ((x[e].w == node) << 3);   // bit q: object 4v+q is on the node
+        if (__ballot_sync(0xFFFFFFFFu, (hits4[0] | hits4[1] | hits4[2] | hits4[3]) != 0) == 0) continue;   // the common trip: nobody in the warp hit
 #pragma unroll
         for (int e = 0; e < 4; e++) {
             const uint64_t v = base + e * stride + threadIdx.x;
-            const uint32_t hits = (x[e].x == node) | ((x[e].y == node) << 1) | ((x[e].z == node) << 2) | ((x[e].w == node) << 3);   // bit q: object 4v+q is on the node
+            const uint32_t hits = hits4[e];
             const unsigned m = __ballot_sync(0xFFFFFFFFu, hits != 0);
             if (m) {                                        // rare: about 4/M of the vectors
                 const unsigned lane = threadIdx.x & 31;
@@ -503,13 +507,15 @@ k_exchange_p2p(const uint32_t *__restrict__ local, XchgPeers peers, uint32_t ran
 }
 
 // The counter exchange AND the bounded-load capacity check of a pass as one single-CTA kernel (bounded_tail.cuh)
-__global__ void __launch_bounds__(1024)
+// 256 threads: 8 warps fit beside the 5 x 8 warps of a resident walk kernel on any SM, so a pipelined check (auxiliary stream) never
+// has to wait for the next set's persistent CTAs to drain
+__global__ void __launch_bounds__(256)
 k_exchange_check(const uint32_t *__restrict__ local, BoundedTail b) { exchange_and_check_block(b, local); }
 
 }  // namespace
 
 void launch_exchange_check(const Launch &L, const uint32_t *d_local, const BoundedTail &b) {
-    k_exchange_check<<<1, 1024, 0, L.stream>>>(d_local, b);
+    k_exchange_check<<<1, 256, 0, L.stream>>>(d_local, b);
     RIO_COUNT_LAUNCH(L);
 }
 

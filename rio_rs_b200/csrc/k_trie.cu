@@ -55,6 +55,13 @@ __device__ __forceinline__ void stage_blob_tma(void *smem_dst, const void *gsrc,
     }
 }
 
+// off' = 2 off + sel as ONE multiply-add: keeps the update on the FMA pipe (the ALU pipe carries the compare and the select)
+__device__ __forceinline__ uint32_t walk_step(uint32_t off, uint32_t sel) {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(r) : "r"(off), "r"(sel));
+    return r;
+}
+
 // One object's walk.  tab32 = thresholds [0, 2^bits) then leaves [2^bits, 2^(bits+1)); the running heap index i starts
 // at 1, so after `bits` contests tab32[i] IS the leaf word.  RIGHT iff u > T3 (u = 2v+1, T3 = max(2T-1, 0)).
 template <int BITS>
@@ -173,7 +180,7 @@ k_assign_trie(const uint64_t *__restrict__ keys, uint64_t n, TrieDev t, uint32_t
                     for (int k = 0; k < OPT; k++) {
                         const uint32_t u = contest_u(o[k], c_lvl_s0[l], c_lvl_m2[l], c_lvl_h2[l]);
                         const uint32_t thr = *reinterpret_cast<const uint32_t *>(tb + off[k]);
-                        off[k] = off[k] + off[k] + (u > thr ? 4u : 0u);
+                        off[k] = walk_step(off[k], u > thr ? 4u : 0u);
                     }
                 }
             } else {
@@ -182,7 +189,7 @@ k_assign_trie(const uint64_t *__restrict__ keys, uint64_t n, TrieDev t, uint32_t
                     for (int k = 0; k < OPT; k++) {
                         const uint32_t u = contest_u(o[k], c_lvl_s0[l], c_lvl_m2[l], c_lvl_h2[l]);
                         const uint32_t thr = *reinterpret_cast<const uint32_t *>(tb + off[k]);
-                        off[k] = off[k] + off[k] + (u > thr ? 4u : 0u);
+                        off[k] = walk_step(off[k], u > thr ? 4u : 0u);
                     }
                 }
             }

@@ -96,6 +96,25 @@ impl GpuObjectPlacement {
         check(self.h(), unsafe { sys::rio_cuda_rebalance(self.h(), if join { sys::RIO_EV_JOIN } else { sys::RIO_EV_LEAVE }, node_idx, &mut moved) })?;
         Ok(moved)
     }
+    /// Solver policy of the handle: `hierarchical = false` is the flat weighted rendezvous (minimal movement, M pair hashes per
+    /// object), `true` is HRW2 (~log2 M contests per object, ~(1 + log2(M)/2)x the minimal movement).
+    pub fn set_solver(&self, hierarchical: bool, trie_bits: u32) -> Result<(), ObjectPlacementError> {
+        check(self.h(), unsafe { sys::rio_cuda_set_solver(self.h(), if hierarchical { sys::RIO_SOLVER_HRW2 } else { sys::RIO_SOLVER_HRW }, trie_bits) })
+    }
+    /// Service::check_address_mismatch (service.rs:261-298) for the owners a batched resolve returned: per entry
+    /// 0 = Ok(()), 1 = Err(Redirect(address)), 2 = clean_server applied + Err(DeallocateServiceObject), 3 = Err(Unknown(malformed)).
+    pub fn check_address_batch(&self, owner_idx: &[u32], self_idx: u32) -> Result<Vec<u8>, ObjectPlacementError> {
+        let mut out = vec![0u8; owner_idx.len()];
+        check(self.h(), unsafe { sys::rio_cuda_check_address_batch(self.h(), owner_idx.as_ptr(), owner_idx.len(), self_idx, out.as_mut_ptr(), ptr::null_mut()) })?;
+        Ok(out)
+    }
+    /// assign_batch followed by the bounded-load rounds (capacity = cap_num/cap_den x fair share); returns (indices, passes).
+    pub fn assign_bounded_batch(&self, keys: &[u64], cap_num: u32, cap_den: u32, max_rounds: u32) -> Result<(Vec<u32>, u32), ObjectPlacementError> {
+        let mut out = vec![sys::RIO_NONE; keys.len()];
+        let mut passes = 0u32;
+        check(self.h(), unsafe { sys::rio_cuda_assign_bounded_batch(self.h(), keys.as_ptr(), keys.len(), 0, cap_num, cap_den, max_rounds, out.as_mut_ptr(), &mut passes) })?;
+        Ok((out, passes))
+    }
     pub fn object_key(id: &ObjectId) -> u64 {
         unsafe { sys::rio_cuda_object_key(id.0.as_ptr() as *const _, id.0.len(), id.1.as_ptr() as *const _, id.1.len()) }
     }
@@ -124,6 +143,25 @@ impl GpuObjectPlacement {
     }
 }
 impl Resolver {
+    /// ObjectPlacement::lookup per id through the coalescing queue (mod.rs:51): node index or RIO_NONE.
+    pub fn lookup_key(&self, key: u64) -> Result<u32, ObjectPlacementError> {
+        let mut idx = sys::RIO_NONE;
+        let st = unsafe { sys::rio_cuda_resolver_lookup(self.raw, key, &mut idx) };
+        if st != sys::RIO_OK {
+            let msg = unsafe { CStr::from_ptr(sys::rio_cuda_resolver_last_error()).to_string_lossy().into_owned() };
+            return Err(if st == sys::RIO_ERR_UPSTREAM { ObjectPlacementError::Upstream(msg) } else { ObjectPlacementError::Unknown(msg) });
+        }
+        Ok(idx)
+    }
+    /// ObjectPlacement::update / remove per id through the coalescing queue (mod.rs:46-49, :55): `idx = RIO_NONE` removes.
+    pub fn update_key(&self, key: u64, idx: u32) -> Result<(), ObjectPlacementError> {
+        let st = unsafe { sys::rio_cuda_resolver_update(self.raw, key, idx) };
+        if st != sys::RIO_OK {
+            let msg = unsafe { CStr::from_ptr(sys::rio_cuda_resolver_last_error()).to_string_lossy().into_owned() };
+            return Err(if st == sys::RIO_ERR_UPSTREAM { ObjectPlacementError::Upstream(msg) } else { ObjectPlacementError::Unknown(msg) });
+        }
+        Ok(())
+    }
     /// Blocking; call it from `spawn_blocking` or a dedicated thread.
     pub fn get_or_create_placement(&self, handler_type: &str, handler_id: &str) -> Result<Option<String>, ObjectPlacementError> {
         let mut buf = vec![0u8; 256];

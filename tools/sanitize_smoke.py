@@ -53,6 +53,38 @@ for k in keys[:50]:
     r.resolve(int(k))
 r.close()
 p.bench_mix_rate(2)                                                 # k_mix_rate
+# ---- HRW2: the trie walk (TMA-staged table, dense / gathered / compare / directory forms), fused exchange + check tail --------
+h2 = R.GpuObjectPlacement(device=0, directory_capacity=1024)
+a5, s5, w5 = O.synth_nodes(130)
+h2.set_nodes(a5[:128], w5[:128])
+for bits in (12, 3, 14):
+    h2.set_solver("hrw2", bits)
+    assert (h2.assign_batch(keys) == O.assign_hrw2(keys, s5[:128], w5[:128], bits=bits)).all()          # k_assign_trie<12|0, smem>, chains at bits 3
+h2.set_solver("hrw2", 12)
+assert (h2.place_batch(keys, "hrw2") == O.assign_hrw2(keys, s5[:128], w5[:128])).all()                   # k_assign_trie_sel
+t5 = h2.new_set(20001)                                                                                   # odd size: the 128-bit load tail
+t5.synth_keys(0, 20001, 3)
+k5 = O.synth_keys(20001, 3)
+assert t5.assign_bounded(0, 5, 4, 4) >= 1                                                                # fused tail (last-CTA ticket, check, mapped flags)
+wi, wc, wp = O.assign_bounded_hrw2(k5, s5[:128], w5[:128], 101, 100, 4)
+assert t5.assign_bounded(0, 101, 100, 4) == wp and (t5.read() == wi).all()                               # spill rounds, masked trie, k_exchange_check
+t5.assign_bounded_begin(0, 5, 4, 4)                                                                      # check on the auxiliary stream
+t5.assign_bounded_end()
+t5.assign()
+t5.commit()
+h2.node_set_active(9, False)
+t5.rebalance("leave", 9)                                                                                 # k_assign_trie compare mode
+h2.rebalance("leave", 9)                                                                                 # k_dir_reassign_trie
+w5b = w5[:128].copy()
+w5b[9] = 0
+assert (t5.read() == O.assign_hrw2(k5, s5[:128], w5b)).all() and (h2.lookup_many(k5) == t5.read()).all()
+v, cleaned = h2.check_address_batch(h2.lookup_many(k5[:3000]), a5[1])                                     # k_check_address (+ clean_flagged when a dead owner is met)
+hb = R.GpuObjectPlacement(device=0)                                                                      # table too large for shared memory: global walk
+a6, s6, w6 = O.synth_nodes(20000)
+hb.set_nodes(a6, w6)
+hb.set_solver("hrw2", 14)
+assert (hb.assign_batch(keys[:2000]) == O.assign_hrw2(keys[:2000], s6, w6, bits=14)).all()
+del hb
 # affinity: CUDA-core kernels always, tensor-core kernel unless --no-umma
 q = R.GpuObjectPlacement(device=0)
 fn = np.random.default_rng(1).uniform(-1, 1, (300, 16)).astype(np.float32)
