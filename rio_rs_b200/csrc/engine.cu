@@ -181,6 +181,8 @@ struct rio_placement {
 
     cudaEvent_t events[RIO_MAX_EVENTS] = {};
     cudaEvent_t ev_pipe[8] = {};
+    cudaEvent_t ev_aux = nullptr;   // recorded behind every capacity check on the auxiliary stream
+    bool aux_used = false;
 
     NcclComm comm = nullptr;
     int rank = 0, world = 1;
@@ -448,7 +450,14 @@ void dir_upsert_dev(rio_placement *h, const uint64_t *d_keys, const uint32_t *d_
 }
 
 // ---- counter exchange: the single collective of the path (all-gather of M u32 per rank, then a sum) -------------
+// Exchanges carry consecutive epochs and must reach the device in epoch order on every rank.  Checks of pipelined calls run on
+// the auxiliary stream; anything that exchanges on the main stream afterwards waits for them first.
+void order_behind_aux_checks(rio_placement *h) {
+    if (h->aux_used) CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_aux, 0));
+}
+
 void exchange_counters(rio_placement *h, const uint32_t *d_local, uint32_t *d_global, uint32_t M) {
+    order_behind_aux_checks(h);
     if (h->world > 1 && h->xchg_ready && M <= h->xchg_nodes) {
         // one kernel: P2P stores into every peer's window + flags over NVLink, no NCCL launch on the critical path
         launch_exchange_p2p(h->L(), d_local, h->xchg_peer, (uint32_t)h->rank, (uint32_t)h->world, M, h->xchg_nodes, ++h->xchg_epoch, d_global);
@@ -588,7 +597,10 @@ std::pair<uint32_t, uint32_t> read_flags(rio_placement *h, BoundedState &bs) {
     const auto t_end = std::chrono::steady_clock::now() + std::chrono::milliseconds(20);
     while (flags[2] != bs.flag_seq) {
         if (std::chrono::steady_clock::now() > t_end) {
+            // slow path (a peer rank is late, first use of the peer mappings, ...): block on both streams the check may be on;
+            // this also surfaces a failed kernel as a CUDA error instead of a missing report
             CUDA_TRY(cudaStreamSynchronize(h->stream));
+            if (h->aux_stream) CUDA_TRY(cudaStreamSynchronize(h->aux_stream));
             REQUIRE(flags[2] == bs.flag_seq, "capacity check did not report (internal error)");
             break;
         }
@@ -647,6 +659,7 @@ void bounded_begin(rio_placement *h, BoundedState &bs, const uint64_t *d_keys, u
         if (!counters_zeroed) CUDA_TRY(cudaMemsetAsync(d_counters, 0, (size_t)std::max(M, 1u) * 4, st));
         const bool p2p = h->world > 1 && h->xchg_ready && M <= h->xchg_nodes;
         if (!pipelined && max_rounds > 1 && h->solver == RIO_SOLVER_HRW2 && (h->world == 1 || p2p)) {
+            order_behind_aux_checks(h);
             const BoundedTail t = make_tail(h, bs, b, M, next_zero, p2p);   // walk + histogram + exchange + check: ONE launch
             launch_assign_trie(h->L(), d_keys, n, h->tabs.trie, d_idx, d_counters, nullptr, 0, h->tabs.tab.n_total, &t);
             fused = true;
@@ -659,7 +672,10 @@ void bounded_begin(rio_placement *h, BoundedState &bs, const uint64_t *d_keys, u
             CUDA_TRY(cudaEventRecord(bs.ev, st));
             CUDA_TRY(cudaStreamWaitEvent(h->aux_stream, bs.ev, 0));
             launch_check(h, bs, d_counters, b, M, next_zero, h->aux_stream);
+            CUDA_TRY(cudaEventRecord(h->ev_aux, h->aux_stream));
+            h->aux_used = true;
         } else {
+            order_behind_aux_checks(h);
             launch_check(h, bs, d_counters, b, M, next_zero, st);
         }
     }
@@ -688,7 +704,7 @@ uint32_t bounded_end(rio_placement *h, BoundedState &bs, const uint64_t *d_keys,
         build_tab(h, h->tabs_masked, &closed);
         if (nsel) run_assign(h, h->solver, h->tabs_masked, d_keys, n, d_idx, d_counters, d_sel, nsel);
         passes++;
-        if (r + 1 < bs.max_rounds) launch_check(h, bs, d_counters, b, M, nullptr, st);
+        if (r + 1 < bs.max_rounds) { order_behind_aux_checks(h); launch_check(h, bs, d_counters, b, M, nullptr, st); }
     }
     return passes;
 }
@@ -778,6 +794,7 @@ rio_status rio_cuda_create(const rio_config *cfg, rio_placement **out) {
         }
         for (auto &ev : h->events) CUDA_TRY(cudaEventCreate(&ev));
         for (auto &ev : h->ev_pipe) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_aux, cudaEventDisableTiming));
         // keep freed blocks in the pool: the scratch buffers are re-used every call
         cudaMemPool_t pool;
         CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
@@ -829,6 +846,7 @@ void rio_cuda_destroy(rio_placement *h) {
     if (h->h_scalars) cudaFreeHost(h->h_scalars);
     for (auto &ev : h->events) if (ev) cudaEventDestroy(ev);
     for (auto &ev : h->ev_pipe) if (ev) cudaEventDestroy(ev);
+    if (h->ev_aux) cudaEventDestroy(h->ev_aux);
     cudaStreamDestroy(h->stream);
     cudaStreamDestroy(h->h2d_stream);
     cudaStreamDestroy(h->d2h_stream);

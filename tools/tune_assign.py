@@ -1,4 +1,5 @@
-"""A/B timing of the compiled tuning points of the rendezvous kernel (development tool; run under gpurun)."""
+"""(needs a library built with RIO_BUILD_TUNING=1: the shipped one carries the default tuning point only)
+A/B timing of the compiled tuning points of the rendezvous kernel (development tool; run under gpurun)."""
 import os
 import sys
 
