@@ -35,7 +35,13 @@ __device__ __forceinline__ void exchange_and_check_block(const BoundedTail &b, c
             asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
             const uint32_t *mine = b.peers.win[rank] + slot_words + threadIdx.x;
             uint32_t v;
-            do { asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory"); } while ((int32_t)(v - epoch) < 0);
+            // polite spin: a pipelined check shares its SM with five walk CTAs of the next set and may wait a whole kernel for the
+            // slowest rank; sleeping between polls leaves that SM's issue slots to the walk (a tight acquire loop cost ~7 % at N = 4)
+            for (;;) {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+                if ((int32_t)(v - epoch) >= 0) break;
+                __nanosleep(256);
+            }
         }
         __syncthreads();
         const volatile uint32_t *src = b.peers.win[rank] + par;

@@ -13,6 +13,8 @@
 #include "spec.cuh"
 #include "bounded_tail.cuh"
 
+#include <cstdlib>
+
 namespace rio {
 
 namespace {
@@ -130,8 +132,8 @@ __device__ __forceinline__ TrieSmem trie_stage(const TrieDev &t, uint32_t hist_b
 // ---- dense assign: thread owns 2 consecutive objects per 128-bit key load, OPT/2 such loads per tile ----------------
 // MODE 0: plain assign (+ fused histogram).  MODE 1: re-assign and compare with the previous assignment (rebalance):
 // only changed indices are written, `moved` counts them.
-template <int BITS, int OPT, int MODE, bool SMEM>
-__global__ void __launch_bounds__(kTrieThreads, SMEM ? 5 : 3)
+template <int BITS, int OPT, int MODE, bool SMEM, int MINB = (SMEM ? 5 : 3)>
+__global__ void __launch_bounds__(kTrieThreads, MINB)
 k_assign_trie(const uint64_t *__restrict__ keys, uint64_t n, TrieDev t, uint32_t *__restrict__ out_idx, uint32_t *__restrict__ counters,
               uint32_t hist_bins, unsigned long long *__restrict__ moved, const __grid_constant__ BoundedTail tail) {
     static_assert(OPT % 2 == 0, "two objects per 128-bit load");
@@ -360,6 +362,29 @@ void launch_assign_trie(const Launch &L, const uint64_t *d_keys, uint64_t n, con
         else RIO_TRIE_LAUNCH(k_assign_trie_sel<false>, grid, sh.smem, d_keys, d_sel, n_work, t, d_out_idx, d_counters, sh.hist_bins);
     } else {
         constexpr int OPT = 4;
+#ifdef RIO_ASSIGN_TUNING   // A/B points of the walk kernel (RIO_BUILD_TUNING=1, tools/tune_trie.py): "<objects per thread><CTAs per SM>"
+        if (const char *tn = getenv("RIO_TRIE_TUNE")) {
+            const int code = atoi(tn);
+            auto go = [&](auto kern, int opt, int minb) {
+                const TrieLaunchShape sh2 = trie_shape(t, d_counters != nullptr, n_total, minb);
+                const uint64_t tiles2 = (n_work + (uint64_t)kTrieThreads * opt - 1) / ((uint64_t)kTrieThreads * opt), cap2 = (uint64_t)L.sm_count * sh2.ctas_per_sm;
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrieSmemBudget + 1024);
+                kern<<<(int)(tiles2 < cap2 ? tiles2 : cap2), kTrieThreads, sh2.smem, L.stream>>>(d_keys, n_work, t, d_out_idx, d_counters, sh2.hist_bins, nullptr, tl);
+            };
+            bool done = true;
+            switch (code) {
+                case 25: go(k_assign_trie<12, 2, 0, true, 5>, 2, 5); break;
+                case 28: go(k_assign_trie<12, 2, 0, true, 8>, 2, 8); break;
+                case 44: go(k_assign_trie<12, 4, 0, true, 4>, 4, 4); break;
+                case 45: go(k_assign_trie<12, 4, 0, true, 5>, 4, 5); break;
+                case 63: go(k_assign_trie<12, 6, 0, true, 3>, 6, 3); break;
+                case 64: go(k_assign_trie<12, 6, 0, true, 4>, 6, 4); break;
+                case 83: go(k_assign_trie<12, 8, 0, true, 3>, 8, 3); break;
+                default: done = false;
+            }
+            if (done && t.bits == 12) { RIO_COUNT_LAUNCH(L); return; }
+        }
+#endif
         const TrieLaunchShape sh = trie_shape(t, d_counters != nullptr, n_total, 5);
         const uint64_t tiles = (n_work + (uint64_t)kTrieThreads * OPT - 1) / ((uint64_t)kTrieThreads * OPT), cap = (uint64_t)L.sm_count * sh.ctas_per_sm;
         const int grid = (int)(tiles < cap ? tiles : cap);
