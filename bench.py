@@ -393,7 +393,14 @@ def main():
     passes = max(passes, run_steps(args.warmup, args.steps))
     p.event_record(1)
     barrier_sync()
-    ms_total = max_over_ranks(p.event_elapsed_ms(0, 1))
+    my_ms = p.event_elapsed_ms(0, 1)
+    ms_total = max_over_ranks(my_ms)
+    per_rank_ms = None
+    if dist:   # diagnostics only: every rank's own device time for the same K steps (the line's value uses the max)
+        t = torch.zeros(world, dtype=torch.float64, device="cuda")
+        t[rank] = my_ms / args.steps
+        dist.all_reduce(t)
+        per_rank_ms = [round(float(x), 6) for x in t.tolist()]
     launches = p.launch_count() - l0
     ms_per_step = ms_total / args.steps
     value = n_global / (ms_per_step * 1e-3)
@@ -596,7 +603,7 @@ def main():
                        "policy": ("hrw2: hierarchical weighted rendezvous, fan-out 2, trie_bits %d (DESIGN.md 3.8)" % TRIE_BITS) if args.policy == "hrw2" else "hrw: flat weighted rendezvous (DESIGN.md 3.4)",
                        "objects_per_gpu": n, "global_objects": n_global, "nodes": M, "weights": "u32 in [1,16], seed 7", "capacity": "1.25", "max_rounds": 4,
                        "passes_run": passes, "passes_in_flight": DEPTH, "l2": "inputs larger than L2: %d resident key sets rotated step to step" % N_SETS, "parallelism": "id-range shard x%d" % world,
-                       "parity_vs_oracle_200k_per_rank": parity_ok, "multi_rank_parity": multi_rank, "device": info["name"], "sms": info["sm_count"]},
+                       "parity_vs_oracle_200k_per_rank": parity_ok, "multi_rank_parity": multi_rank, "per_rank_ms_per_step": per_rank_ms, "device": info["name"], "sms": info["sm_count"]},
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peak, "unit": "GB/s", "frac": achieved_gbs / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": kernel_name, "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_OBJECT * n, "peak_source": peak_src,
                          "note": "12 B/object (8 B key in, 4 B node index out); the walk is bound by shared-memory gather wavefronts and the ALU pipe before HBM (profiles/r02_ncu_trie.json)"
