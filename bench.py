@@ -530,12 +530,14 @@ def main():
                 t.synth_keys(lo, hi - lo, 1 + k)
                 ts.append(t)
 
+            SD = min(DEPTH, len(ts) - 1)   # a set takes one bounded call at a time
+
             def strong_steps(k):
                 for i in range(k):
                     ts[i % 3].assign_bounded_begin(N_OBJECTS, 5, 4, 4)
-                    if i >= DEPTH:
-                        ts[(i - DEPTH) % 3].assign_bounded_end()
-                for i in range(max(0, k - DEPTH), k):
+                    if i >= SD:
+                        ts[(i - SD) % 3].assign_bounded_end()
+                for i in range(max(0, k - SD), k):
                     ts[i % 3].assign_bounded_end()
 
             strong_steps(20)
@@ -549,7 +551,7 @@ def main():
             ok = all_ranks_ok((ts[0].read(0, min(hi - lo, 100_000)) == oracle_assign(O.synth_keys(min(hi - lo, 100_000), 1, first=lo), args.policy)).all())
             extra["C4_strong_10M_total"] = {"ms_per_step": ms, "placements_per_s": N_OBJECTS / (ms * 1e-3), "objects_per_rank": hi - lo, "steps": sreps, "parity_vs_oracle": ok,
                                             "note": "BASELINE configs[3] as worded: 10 M objects TOTAL, id-range sharded over the ranks; three resident key sets rotated (L2-resident at N >= 2), "
-                                                    "%d passes in flight; strong-scaling efficiency = (this at N) / (N x this at N=1)" % DEPTH}
+                                                    "%d passes in flight; strong-scaling efficiency = (this at N) / (N x this at N=1)" % SD}
             del ts, t
             # C5: 100 M objects total, the fixed list of 8 join/leave events, one exchange of the counters per event
             lo, hi = parallel.shard_range(100_000_000, rank, world)

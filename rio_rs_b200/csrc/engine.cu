@@ -288,24 +288,23 @@ void build_tab(rio_placement *h, TabBufs &tb, const std::vector<uint8_t> *closed
     for (uint32_t i = nb - 1; i >= 1; i--) wsum[i] = wsum[2 * i] + wsum[2 * i + 1];
     std::vector<uint32_t> tab32((size_t)2 * nb, 0);
     for (uint32_t i = 1; i < nb; i++) tab32[i] = contest_t3(wsum[2 * i], wsum[2 * i + 1]);
-    std::vector<uint4> crec;
-    std::vector<uint32_t> cnidx;
+    std::vector<uint4> crec;                                       // two per chain member: the contest record, then {node index, 0, 0, 0}
+    const uint32_t off_crec = (uint32_t)((tab32.size() * 4 + 15) / 16 * 16);
     for (uint32_t k = 0; k < nb; k++) {
         const uint32_t lo = bstart[k], hi = bstart[k + 1];
         if (lo == hi) { tab32[nb + k] = kNone; continue; }
         if (hi - lo == 1) { tab32[nb + k] = mem[lo].idx; continue; }
-        tab32[nb + k] = 0x80000000u | (uint32_t)crec.size();
+        tab32[nb + k] = 0x80000000u | (off_crec + (uint32_t)crec.size() * 16u);   // byte offset of the chain's first record in the blob
         uint64_t rest = wsum[nb + k];
-        for (uint32_t q = lo; q < hi; q++) {
+        for (uint32_t q = lo; q + 1 < hi; q++) {                                  // the last member needs no record: it is always taken
             rest -= mem[q].w;
             const ContestRec r = contest_rec(h->nodes[mem[q].idx].seed);
-            crec.push_back(make_uint4(r.s0, r.m2, r.h2, q + 1 == hi ? 0xFFFFFFFFu : contest_t3(mem[q].w, rest)));
-            cnidx.push_back(mem[q].idx);
+            crec.push_back(make_uint4(r.s0, r.m2, r.h2, contest_t3(mem[q].w, rest)));
+            const uint32_t next = q + 2 == hi ? mem[hi - 1].idx : 0x80000000u | (off_crec + (uint32_t)(crec.size() + 1) * 16u);
+            crec.push_back(make_uint4(mem[q].idx, next, 0, 0));
         }
     }
-    const uint32_t off_crec = (uint32_t)((tab32.size() * 4 + 15) / 16 * 16);
-    const uint32_t off_cnidx = off_crec + (uint32_t)crec.size() * 16;
-    const uint32_t blob_bytes = std::max<uint32_t>(16u, (uint32_t)((off_cnidx + cnidx.size() * 4 + 15) / 16 * 16));
+    const uint32_t blob_bytes = std::max<uint32_t>(16u, off_crec + (uint32_t)crec.size() * 16u);
     // the policy's view of every interned node (service.rs:226-231 asks is_active only: a draining node -- active, weight 0 --
     // keeps its objects) and the solver's (active and weight > 0)
     std::vector<uint8_t> state(n_total ? n_total : 1, 0);
@@ -335,14 +334,15 @@ void build_tab(rio_placement *h, TabBufs &tb, const std::vector<uint8_t> *closed
     memcpy(tb.stage + o_classes, classes.data(), classes.size() * sizeof(ClassRec));
     memcpy(tb.stage + o_byidx, by_idx.data(), by_idx.size() * sizeof(uint4));
     memcpy(tb.stage + o_trie, tab32.data(), tab32.size() * 4);
-    if (!crec.empty()) { memcpy(tb.stage + o_trie + off_crec, crec.data(), crec.size() * 16); memcpy(tb.stage + o_trie + off_cnidx, cnidx.data(), cnidx.size() * 4); }
+    if (!crec.empty()) memcpy(tb.stage + o_trie + off_crec, crec.data(), crec.size() * 16);
     memcpy(tb.stage + o_state, state.data(), state.size());
     memcpy(tb.stage + o_live, livef.data(), livef.size() * 4);
     tb.dev.ensure(total, st);
     CUDA_TRY(cudaMemcpyAsync(tb.dev.p, tb.stage, total, cudaMemcpyHostToDevice, st));
     tb.upload_pending = true;
     unsigned char *d = tb.dev.as<unsigned char>();
-    tb.trie = TrieDev{d + o_trie, blob_bytes, off_crec, off_cnidx, bits, (uint32_t)crec.size()};
+    tb.trie = TrieDev{d + o_trie, blob_bytes, off_crec, bits, (uint32_t)crec.size() / 2, {}};
+    for (uint32_t i = 1; i < 8 && i < nb; i++) tb.trie.top[i] = tab32[i];
     tb.tab.recs = reinterpret_cast<const NodeRec *>(d + o_recs);
     tb.tab.classes = reinterpret_cast<const ClassRec *>(d + o_classes);
     tb.tab.by_idx = reinterpret_cast<const uint4 *>(d + o_byidx);

@@ -84,25 +84,30 @@ __device__ __forceinline__ uint32_t trie_leaf_index(ObjHash o, const uint32_t *_
     return i;
 }
 
-// leaf word: kNone = empty bucket (only without live nodes), top bit = chain start, else the node index
-__device__ __forceinline__ uint32_t trie_resolve_leaf(ObjHash o, uint32_t leaf, const uint4 *__restrict__ crec, const uint32_t *__restrict__ cnidx) {
-    if (leaf == kNone || !(leaf & 0x80000000u)) return leaf;
-    uint32_t pos = leaf & 0x7FFFFFFFu;
-    for (;;) {   // the last member of a chain carries T3 = 0xFFFFFFFF: always taken
-        const uint4 r = crec[pos];
-        if (contest_u(o, r.x, r.y, r.z) <= r.w) return cnidx[pos];
-        pos++;
+// leaf word: kNone = empty bucket (only without live nodes), top bit = chain start (low bits: BYTE offset of the first
+// chain record inside the blob), else the node index.  A chain of k members has k-1 records of 32 bytes:
+// {s0, m2, h2, T3} {this member's node index, next, 0, 0}; `next` is the LAST member's node index when only that one is
+// left (it would always be taken) and 0x80000000 | byte offset of the next record otherwise.
+__device__ __forceinline__ uint32_t trie_resolve_leaf(ObjHash o, uint32_t leaf, const unsigned char *__restrict__ blob) {
+    if ((int32_t)leaf > -2) return leaf;           // node index (top bit clear) or kNone
+    uint32_t w = leaf;
+    for (;;) {
+        const unsigned char *p = blob + (w & 0x7FFFFFFFu);
+        const uint4 r = *reinterpret_cast<const uint4 *>(p);
+        const uint2 nn = *reinterpret_cast<const uint2 *>(p + 16);
+        if (contest_u(o, r.x, r.y, r.z) <= r.w) return nn.x;
+        if ((int32_t)nn.y >= 0) return nn.y;
+        w = nn.y;
     }
 }
 
 struct TrieSmem {
-    const uint32_t *tab32;
-    const uint4 *crec;
-    const uint32_t *cnidx;
+    const uint32_t *tab32;          // == the blob: thresholds, leaves, then the chain records
+    const unsigned char *blob;
     uint32_t *hist;
 };
 
-// Shared-memory layout: [blob (tab32 | crec | cnidx)] [hist bins] [mbarrier].  Falls back to the table in global memory
+// Shared-memory layout: [blob (tab32 | chain records)] [hist bins] [mbarrier].  Falls back to the table in global memory
 // (through the read-only path) when the blob does not fit beside the histogram.
 template <bool SMEM>
 __device__ __forceinline__ TrieSmem trie_stage(const TrieDev &t, uint32_t hist_bins) {
@@ -112,14 +117,12 @@ __device__ __forceinline__ TrieSmem trie_stage(const TrieDev &t, uint32_t hist_b
     uint32_t off = 0;
     if (in_smem) {
         s.tab32 = reinterpret_cast<const uint32_t *>(smem_trie);
-        s.crec = reinterpret_cast<const uint4 *>(smem_trie + t.off_crec);
-        s.cnidx = reinterpret_cast<const uint32_t *>(smem_trie + t.off_cnidx);
+        s.blob = smem_trie;
         off = t.blob_bytes;
     } else {
         const unsigned char *g = reinterpret_cast<const unsigned char *>(t.blob);
         s.tab32 = reinterpret_cast<const uint32_t *>(g);
-        s.crec = reinterpret_cast<const uint4 *>(g + t.off_crec);
-        s.cnidx = reinterpret_cast<const uint32_t *>(g + t.off_cnidx);
+        s.blob = g;
     }
     s.hist = reinterpret_cast<uint32_t *>(smem_trie + off);
     for (uint32_t j = threadIdx.x; j < hist_bins; j += blockDim.x) s.hist[j] = 0;
@@ -138,7 +141,6 @@ k_assign_trie(const uint64_t *__restrict__ keys, uint64_t n, TrieDev t, uint32_t
               uint32_t hist_bins, unsigned long long *__restrict__ moved, const __grid_constant__ BoundedTail tail) {
     static_assert(OPT % 2 == 0, "two objects per 128-bit load");
     constexpr bool in_smem = SMEM;
-    const TrieSmem s = trie_stage<SMEM>(t, hist_bins);
     constexpr int SEG = OPT / 2;
     const uint64_t tile_objs = (uint64_t)kTrieThreads * OPT;
     const uint64_t n_tiles = (n + tile_objs - 1) / tile_objs;
@@ -146,23 +148,31 @@ k_assign_trie(const uint64_t *__restrict__ keys, uint64_t n, TrieDev t, uint32_t
     // keys of the NEXT tile are requested before the current tile is walked: the walk (~170 instructions per object)
     // hides the HBM latency of the stream even at 5 CTAs per SM
     ulonglong2 kk[SEG];
+    // A tile that lies wholly inside [0, n) -- all but the last -- takes the straight path: no per-load / per-store bound checks
     auto load_tile = [&](uint64_t tile) {
+        const uint64_t f0 = tile * tile_objs + 2 * threadIdx.x;
+        if ((tile + 1) * tile_objs <= n) {
+            const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(keys + f0);   // keys is 256-byte aligned, f0 is even
+#pragma unroll
+            for (int g = 0; g < SEG; g++) kk[g] = __ldg(src + g * kTrieThreads);
+            return;
+        }
 #pragma unroll
         for (int g = 0; g < SEG; g++) {
-            const uint64_t f = tile * tile_objs + (uint64_t)g * (2 * kTrieThreads) + 2 * threadIdx.x;
+            const uint64_t f = f0 + (uint64_t)g * (2 * kTrieThreads);
             kk[g] = make_ulonglong2(0, 0);
-            if (f + 1 < n) kk[g] = __ldg(reinterpret_cast<const ulonglong2 *>(keys + f));   // keys is 256-byte aligned, f is even
+            if (f + 1 < n) kk[g] = __ldg(reinterpret_cast<const ulonglong2 *>(keys + f));
             else if (f < n) kk[g].x = __ldg(keys + f);
         }
     };
-    if (blockIdx.x < n_tiles) load_tile(blockIdx.x);
+    if (blockIdx.x < n_tiles) load_tile(blockIdx.x);                 // the first keys are in flight while the table is staged
+    const TrieSmem s = trie_stage<SMEM>(t, hist_bins);
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint64_t base = tile * tile_objs;
+        const bool full_tile = base + tile_objs <= n;
         ObjHash o[OPT];
-        uint64_t first[SEG];
 #pragma unroll
         for (int g = 0; g < SEG; g++) {
-            first[g] = base + (uint64_t)g * (2 * kTrieThreads) + 2 * threadIdx.x;
             o[2 * g] = obj_hash(kk[g].x);
             o[2 * g + 1] = obj_hash(kk[g].y);
         }
@@ -176,8 +186,21 @@ k_assign_trie(const uint64_t *__restrict__ keys, uint64_t n, TrieDev t, uint32_t
             for (int k = 0; k < OPT; k++) off[k] = 4;
             // level-major: the OPT walks of a thread interleave, so every LDS has OPT-1 independent ones behind it
             if (BITS > 0) {
+                // The seven thresholds of levels 0-2 travel as kernel parameters (constant bank, uniform registers): those
+                // contests cost selects instead of shared-memory wavefronts -- the LDS data pipe is this kernel's limiter
+                constexpr int TOP = BITS >= 3 ? 3 : 0;
+                if (TOP) {
 #pragma unroll
-                for (int l = 0; l < BITS; l++) {
+                    for (int k = 0; k < OPT; k++) {
+                        const bool c0 = contest_u(o[k], c_lvl_s0[0], c_lvl_m2[0], c_lvl_h2[0]) > t.top[1];
+                        const bool c1 = contest_u(o[k], c_lvl_s0[1], c_lvl_m2[1], c_lvl_h2[1]) > (c0 ? t.top[3] : t.top[2]);
+                        const uint32_t t2 = c0 ? (c1 ? t.top[7] : t.top[6]) : (c1 ? t.top[5] : t.top[4]);
+                        const bool c2 = contest_u(o[k], c_lvl_s0[2], c_lvl_m2[2], c_lvl_h2[2]) > t2;
+                        off[k] = 32u + (c0 ? 16u : 0u) + (c1 ? 8u : 0u) + (c2 ? 4u : 0u);
+                    }
+                }
+#pragma unroll
+                for (int l = TOP; l < BITS; l++) {
 #pragma unroll
                     for (int k = 0; k < OPT; k++) {
                         const uint32_t u = contest_u(o[k], c_lvl_s0[l], c_lvl_m2[l], c_lvl_h2[l]);
@@ -203,24 +226,41 @@ k_assign_trie(const uint64_t *__restrict__ keys, uint64_t n, TrieDev t, uint32_t
         }
         uint32_t nid[OPT];
 #pragma unroll
-        for (int k = 0; k < OPT; k++) nid[k] = trie_resolve_leaf(o[k], leaf[k], s.crec, s.cnidx);
+        for (int k = 0; k < OPT; k++) nid[k] = trie_resolve_leaf(o[k], leaf[k], s.blob);
+        if (MODE == 0 && full_tile) {
+            uint2 *dst = reinterpret_cast<uint2 *>(out_idx + base + 2 * threadIdx.x);
+#pragma unroll
+            for (int g = 0; g < SEG; g++) dst[g * kTrieThreads] = make_uint2(nid[2 * g], nid[2 * g + 1]);
+            // kNone leaves exist only when NO node is live (the walk never enters an empty subtree otherwise): one test covers the tile
+            if (counters && nid[0] != kNone) {
+                if (hist_bins) {
+#pragma unroll
+                    for (int k = 0; k < OPT; k++) atomicAdd(&s.hist[nid[k]], 1u);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < OPT; k++) atomicAdd(&counters[nid[k]], 1u);
+                }
+            }
+            continue;
+        }
 #pragma unroll
         for (int g = 0; g < SEG; g++) {
-            if (first[g] >= n) continue;
-            const bool two = first[g] + 1 < n;
+            const uint64_t first = base + (uint64_t)g * (2 * kTrieThreads) + 2 * threadIdx.x;
+            if (first >= n) continue;
+            const bool two = first + 1 < n;
             if (MODE == 1) {
                 uint2 old = make_uint2(kNone, kNone);
-                if (two) old = *reinterpret_cast<const uint2 *>(out_idx + first[g]);
-                else old.x = out_idx[first[g]];
+                if (two) old = *reinterpret_cast<const uint2 *>(out_idx + first);
+                else old.x = out_idx[first];
                 const bool c0 = old.x != nid[2 * g], c1 = two && old.y != nid[2 * g + 1];
                 if (c0 | c1) {
-                    if (two) *reinterpret_cast<uint2 *>(out_idx + first[g]) = make_uint2(nid[2 * g], nid[2 * g + 1]);
-                    else out_idx[first[g]] = nid[2 * g];
+                    if (two) *reinterpret_cast<uint2 *>(out_idx + first) = make_uint2(nid[2 * g], nid[2 * g + 1]);
+                    else out_idx[first] = nid[2 * g];
                 }
                 n_moved += (unsigned)c0 + (unsigned)c1;
             } else {
-                if (two) *reinterpret_cast<uint2 *>(out_idx + first[g]) = make_uint2(nid[2 * g], nid[2 * g + 1]);
-                else out_idx[first[g]] = nid[2 * g];
+                if (two) *reinterpret_cast<uint2 *>(out_idx + first) = make_uint2(nid[2 * g], nid[2 * g + 1]);
+                else out_idx[first] = nid[2 * g];
             }
             if (counters) {
                 if (hist_bins) {
@@ -268,7 +308,7 @@ k_assign_trie_sel(const uint64_t *__restrict__ keys, const uint32_t *__restrict_
         const uint32_t oi = __ldg(sel + q);
         const ObjHash o = obj_hash(__ldg(keys + oi));
         const uint32_t i = trie_leaf_index<0>(o, s.tab32, t.bits);
-        const uint32_t nid = trie_resolve_leaf(o, s.tab32[i], s.crec, s.cnidx);
+        const uint32_t nid = trie_resolve_leaf(o, s.tab32[i], s.blob);
         out_idx[oi] = nid;
         if (counters && nid != kNone) { if (hist_bins) atomicAdd(&s.hist[nid], 1u); else atomicAdd(&counters[nid], 1u); }
     }
@@ -293,7 +333,7 @@ k_dir_reassign_trie(DirDev dir, TrieDev t, unsigned long long *__restrict__ move
         if (key == kEmptyKey || v.z == kNone) continue;
         const ObjHash o = obj_hash(key);
         const uint32_t li = trie_leaf_index<0>(o, s.tab32, t.bits);
-        const uint32_t nid = trie_resolve_leaf(o, s.tab32[li], s.crec, s.cnidx);
+        const uint32_t nid = trie_resolve_leaf(o, s.tab32[li], s.blob);
         if (nid != v.z) { reinterpret_cast<uint32_t *>(&dir.slots[i].val)[0] = nid; n_moved++; }
     }
 #pragma unroll

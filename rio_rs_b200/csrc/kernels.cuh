@@ -30,15 +30,17 @@ struct NodeTabDev {
 
 // ---- HRW2 table: one contiguous blob, staged into shared memory by ONE cp.async.bulk ---------
 //   [0, 4 << bits)                 thresholds T3 of the trie nodes, heap order (index 1 = root; [0] unused)
-//   [4 << bits, 8 << bits)         leaf words, one per bucket: node index | 0x80000000 + chain start | kNone (empty)
-//   off_crec  (16-byte aligned)    chain records {s0, m2, h2, T3}: member-keyed contests inside multi-node buckets
-//   off_cnidx                      node index of each chain record
+//   [4 << bits, 8 << bits)         leaf words, one per bucket: node index | 0x80000000 + byte offset of the chain's first record | kNone (empty)
+//   off_crec  (16-byte aligned)    chain records, 32 bytes each, k-1 for a bucket of k nodes: {s0, m2, h2, T3} (the member-keyed
+//                                  contest) then {this node's index, next, 0, 0}; next = the last node's index, or 0x80000000 + byte
+//                                  offset of the next record
 struct TrieDev {
     const void *blob;
     uint32_t blob_bytes;   // multiple of 16
-    uint32_t off_crec, off_cnidx;
+    uint32_t off_crec;     // chain records start here (32 bytes per chain member); leaf words hold byte offsets into the blob
     uint32_t bits;
     uint32_t n_chain;
+    uint32_t top[8];       // copy of the thresholds at heap indices 1..7 (levels 0-2): read from the parameter bank by the dense kernel
 };
 
 // ---- directory: open addressing, 16-byte AoS slots ------------------------------------------------------
