@@ -608,7 +608,7 @@ def main():
                        "parity_vs_oracle_200k_per_rank": parity_ok, "multi_rank_parity": multi_rank, "per_rank_ms_per_step": per_rank_ms, "device": info["name"], "sms": info["sm_count"]},
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peak, "unit": "GB/s", "frac": achieved_gbs / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": kernel_name, "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_OBJECT * n, "peak_source": peak_src,
-                         "note": "12 B/object (8 B key in, 4 B node index out); the walk is bound by shared-memory gather wavefronts and the ALU pipe before HBM (profiles/r02_ncu_trie.json)"
+                         "note": "12 B/object (8 B key in, 4 B node index out); the walk is bound by the shared-memory data pipe (random trie gathers: 76 % of peak wavefronts over the launch, 83 % while the SMs are active) with the issue slots next (75 %), HBM third (profiles/r02_ncu_trie.json, DESIGN.md 5.4)"
                          if args.policy == "hrw2" else "integer-ALU bound by construction (1024 pair hashes per 12 B); see policies.hrw.alu_roofline"},
             "policies": policies,
             "cpu_baseline": cpu,

@@ -192,7 +192,8 @@ struct rio_placement {
     uint32_t xchg_nodes = 0, xchg_epoch = 0;
     bool xchg_ready = false;
 
-    Launch L() { return Launch{stream, sm_count, &launches}; }
+    int walk_spare = 0;   // set around a pipelined pass: the walk leaves one CTA slot free for the check kernel of the previous pass
+    Launch L() { return Launch{stream, sm_count, &launches, walk_spare}; }
     uint32_t *d_error() { return reinterpret_cast<uint32_t *>(d_scalars + S_COUNT); }
 };
 
@@ -664,7 +665,12 @@ void bounded_begin(rio_placement *h, BoundedState &bs, const uint64_t *d_keys, u
             launch_assign_trie(h->L(), d_keys, n, h->tabs.trie, d_idx, d_counters, nullptr, 0, h->tabs.tab.n_total, &t);
             fused = true;
         } else {
+            // pipelined: five walk CTAs per SM leave no room for the 256-thread check kernel of the previous pass, which then takes
+            // the slot of one of THIS pass's CTAs at the kernel boundary and delays it; one spare slot on the machine avoids that
+            static const int spare = [] { const char *e = getenv("RIO_TRIE_SPARE"); return e ? atoi(e) : 1; }();
+            h->walk_spare = (pipelined && max_rounds > 1) ? spare : 0;
             run_assign(h, h->solver, h->tabs, d_keys, n, d_idx, d_counters, nullptr, 0);
+            h->walk_spare = 0;
         }
     }
     if (!fused && max_rounds > 1) {

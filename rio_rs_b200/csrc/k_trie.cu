@@ -165,8 +165,14 @@ k_assign_trie(const uint64_t *__restrict__ keys, uint64_t n, TrieDev t, uint32_t
             else if (f < n) kk[g].x = __ldg(keys + f);
         }
     };
-    if (blockIdx.x < n_tiles) load_tile(blockIdx.x);                 // the first keys are in flight while the table is staged
+    // Programmatic dependent launch: this grid may be scheduled while the previous kernel of the stream is still draining.  The
+    // table (written by copies only, never by a kernel) is staged first; nothing a previous KERNEL may have produced -- keys,
+    // counters, indices -- is touched before griddepcontrol.wait, which returns once that kernel has completed and flushed.
+    // Both instructions are no-ops for a launch without the attribute.
     const TrieSmem s = trie_stage<SMEM>(t, hist_bins);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (blockIdx.x < n_tiles) load_tile(blockIdx.x);
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint64_t base = tile * tile_objs;
         const bool full_tile = base + tile_objs <= n;
@@ -388,6 +394,28 @@ uint64_t trie_wave_objects(int sm_count) { return (uint64_t)sm_count * 5 * kTrie
         KERNEL<<<(GRID), kTrieThreads, (SMEM), L.stream>>>(__VA_ARGS__);                                               \
     } while (0)
 
+// The dense walk is launched with programmatic stream serialization: its CTAs take the SM slots the previous kernel's CTAs free
+// one by one and stage their table while that kernel drains (RIO_TRIE_PDL=0 turns the attribute off, for A/B runs).
+#define RIO_TRIE_LAUNCH_PDL(KERNEL, GRID, SMEM, ...)                                                                   \
+    do {                                                                                                               \
+        static bool attr_set[64] = {};                                                                                 \
+        static const bool pdl = [] { const char *e = getenv("RIO_TRIE_PDL"); return !(e && e[0] == '0'); }();          \
+        int dev__ = 0;                                                                                                 \
+        cudaGetDevice(&dev__);                                                                                         \
+        if (dev__ < 0 || dev__ >= 64 || !attr_set[dev__]) {                                                            \
+            cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrieSmemBudget + 1024);    \
+            if (dev__ >= 0 && dev__ < 64) attr_set[dev__] = true;                                                      \
+        }                                                                                                              \
+        cudaLaunchConfig_t cfg__ = {};                                                                                 \
+        cfg__.gridDim = dim3((unsigned)(GRID)); cfg__.blockDim = dim3(kTrieThreads);                                   \
+        cfg__.dynamicSmemBytes = (SMEM); cfg__.stream = L.stream;                                                      \
+        cudaLaunchAttribute at__[1];                                                                                   \
+        at__[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                               \
+        at__[0].val.programmaticStreamSerializationAllowed = 1;                                                        \
+        cfg__.attrs = at__; cfg__.numAttrs = pdl ? 1 : 0;                                                              \
+        cudaLaunchKernelEx(&cfg__, KERNEL, __VA_ARGS__);                                                               \
+    } while (0)
+
 void launch_assign_trie(const Launch &L, const uint64_t *d_keys, uint64_t n, const TrieDev &t, uint32_t *d_out_idx, uint32_t *d_counters,
                         const uint32_t *d_sel, uint64_t n_sel, uint32_t n_total, const BoundedTail *tail) {
     BoundedTail no_tail{};
@@ -426,11 +454,14 @@ void launch_assign_trie(const Launch &L, const uint64_t *d_keys, uint64_t n, con
         }
 #endif
         const TrieLaunchShape sh = trie_shape(t, d_counters != nullptr, n_total, 5);
-        const uint64_t tiles = (n_work + (uint64_t)kTrieThreads * OPT - 1) / ((uint64_t)kTrieThreads * OPT), cap = (uint64_t)L.sm_count * sh.ctas_per_sm;
+        uint64_t cap = (uint64_t)L.sm_count * sh.ctas_per_sm;
+        if (L.spare_ctas > 0 && cap > (uint64_t)L.spare_ctas + 1) cap -= (uint64_t)L.spare_ctas;
+        const uint64_t tiles = (n_work + (uint64_t)kTrieThreads * OPT - 1) / ((uint64_t)kTrieThreads * OPT);
         const int grid = (int)(tiles < cap ? tiles : cap);
-        if (!sh.in_smem) RIO_TRIE_LAUNCH((k_assign_trie<0, OPT, 0, false>), grid, sh.smem, d_keys, n_work, t, d_out_idx, d_counters, sh.hist_bins, nullptr, tl);
-        else if (t.bits == 12) RIO_TRIE_LAUNCH((k_assign_trie<12, OPT, 0, true>), grid, sh.smem, d_keys, n_work, t, d_out_idx, d_counters, sh.hist_bins, nullptr, tl);
-        else RIO_TRIE_LAUNCH((k_assign_trie<0, OPT, 0, true>), grid, sh.smem, d_keys, n_work, t, d_out_idx, d_counters, sh.hist_bins, nullptr, tl);
+        unsigned long long *no_moved = nullptr;
+        if (!sh.in_smem) RIO_TRIE_LAUNCH_PDL((k_assign_trie<0, OPT, 0, false>), grid, sh.smem, d_keys, n_work, t, d_out_idx, d_counters, sh.hist_bins, no_moved, tl);
+        else if (t.bits == 12) RIO_TRIE_LAUNCH_PDL((k_assign_trie<12, OPT, 0, true>), grid, sh.smem, d_keys, n_work, t, d_out_idx, d_counters, sh.hist_bins, no_moved, tl);
+        else RIO_TRIE_LAUNCH_PDL((k_assign_trie<0, OPT, 0, true>), grid, sh.smem, d_keys, n_work, t, d_out_idx, d_counters, sh.hist_bins, no_moved, tl);
     }
     RIO_COUNT_LAUNCH(L);
 }

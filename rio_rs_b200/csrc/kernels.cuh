@@ -57,7 +57,7 @@ struct DirDev {
     uint32_t shift;     // 64 - log2(capacity)
 };
 
-struct Launch { cudaStream_t stream; int sm_count; uint64_t *launch_counter; };
+struct Launch { cudaStream_t stream; int sm_count; uint64_t *launch_counter; int spare_ctas = 0; /* dense walk: leave this many CTA slots of the machine free */ };
 
 // ---- the tail of a bounded-load pass: counter exchange + capacity check (bounded_tail.cuh) ----------------------------------
 struct XchgPeers { uint32_t *win[16]; };
