@@ -668,9 +668,9 @@ void bounded_begin(rio_placement *h, BoundedState &bs, const uint64_t *d_keys, u
             // pipelined: five walk CTAs per SM leave no room for the 256-thread check kernel of the previous pass, which then takes
             // the slot of one of THIS pass's CTAs at the kernel boundary and delays it; one spare slot on the machine avoids that
             static const int spare = [] { const char *e = getenv("RIO_TRIE_SPARE"); return e ? atoi(e) : 1; }();
+            struct SpareScope { int &v; ~SpareScope() { v = 0; } } scope{h->walk_spare};   // also reset when the launch throws
             h->walk_spare = (pipelined && max_rounds > 1) ? spare : 0;
             run_assign(h, h->solver, h->tabs, d_keys, n, d_idx, d_counters, nullptr, 0);
-            h->walk_spare = 0;
         }
     }
     if (!fused && max_rounds > 1) {
