@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "librio_cuda.so")
 SOURCES = ["k_assign.cu", "k_trie.cu", "k_affinity_umma.cu", "k_directory.cu", "engine.cu", "resolver.cu", "durable.cu"]
-HEADERS = ["kernels.cuh", "spec.cuh", "bounded_tail.cuh", os.path.join("..", "..", "include", "rio_cuda.h"), os.path.join("..", "..", "include", "rio_cuda_dev.h")]
+HEADERS = ["kernels.cuh", "spec.cuh", "bounded_tail.cuh", "trie_table.hpp", os.path.join("..", "..", "include", "rio_cuda.h"), os.path.join("..", "..", "include", "rio_cuda_dev.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

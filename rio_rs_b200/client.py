@@ -20,7 +20,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "librio_client.so")
 SRC = os.path.join(HERE, "csrc", "client.cpp")
-DEPS = [SRC, os.path.join(HERE, "csrc", "spec.cuh"), os.path.join(HERE, "..", "include", "rio_client.h")]
+DEPS = [SRC, os.path.join(HERE, "csrc", "spec.cuh"), os.path.join(HERE, "csrc", "trie_table.hpp"), os.path.join(HERE, "..", "include", "rio_client.h")]
 NONE = 0xFFFFFFFF
 _lib = None
 

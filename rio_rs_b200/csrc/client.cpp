@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "spec.cuh"
+#include "trie_table.hpp"
 
 using namespace rio;
 
@@ -17,12 +18,11 @@ struct rio_client_ring {
     std::vector<Node> nodes;
     std::vector<uint64_t> seed;
     std::vector<uint32_t> weight;
-    // HRW2: thresholds of the binary trie over node positions in heap order, one leaf word per bucket, and the
-    // member-keyed chain records of buckets that hold more than one node -- the same table the servers' kernels walk
+    // HRW2: the table blob -- thresholds of the binary trie over node positions in heap order, one leaf word per
+    // bucket, member-keyed chain records -- built by the SAME function the servers use for the table their kernels walk
+    // (trie_table.hpp), and walked here by the host form of the kernel's walk
     uint32_t policy = RIO_CLIENT_POLICY_HRW, bits = 12;
-    std::vector<uint32_t> tab32;                       // [0, 2^bits) thresholds T3, [2^bits, 2^(bits+1)) leaf words
-    struct Chain { uint32_t s0, m2, h2, t3, idx; };
-    std::vector<Chain> chain;
+    TrieBlob trie;
     std::vector<ContestRec> level;
 };
 
@@ -43,45 +43,14 @@ uint32_t first_hop(const rio_client_ring &r, uint64_t key) {
 }
 
 void build_trie(rio_client_ring &r) {
-    const uint32_t bits = r.bits, nb = 1u << bits;
-    struct Mem { uint64_t pos; uint32_t idx, w; };
-    std::vector<Mem> mem;
-    for (uint32_t j = 0; j < (uint32_t)r.seed.size(); j++) if (r.weight[j]) mem.push_back(Mem{mix64(r.seed[j] ^ kSaltPos), j, r.weight[j]});
-    std::sort(mem.begin(), mem.end(), [](const Mem &a, const Mem &b) { return a.pos != b.pos ? a.pos < b.pos : a.idx < b.idx; });
-    std::vector<uint64_t> wsum((size_t)2 * nb, 0);
-    std::vector<uint32_t> bstart((size_t)nb + 1, 0);
-    for (const Mem &m : mem) { const uint32_t bk = bits ? (uint32_t)(m.pos >> (64 - bits)) : 0u; wsum[nb + bk] += m.w; bstart[bk + 1]++; }
-    for (uint32_t k = 0; k < nb; k++) bstart[k + 1] += bstart[k];
-    for (uint32_t i = nb - 1; i >= 1; i--) wsum[i] = wsum[2 * i] + wsum[2 * i + 1];
-    r.tab32.assign((size_t)2 * nb, 0);
-    for (uint32_t i = 1; i < nb; i++) r.tab32[i] = contest_t3(wsum[2 * i], wsum[2 * i + 1]);
-    r.chain.clear();
-    for (uint32_t k = 0; k < nb; k++) {
-        const uint32_t lo = bstart[k], hi = bstart[k + 1];
-        if (lo == hi) { r.tab32[nb + k] = kNone; continue; }
-        if (hi - lo == 1) { r.tab32[nb + k] = mem[lo].idx; continue; }
-        r.tab32[nb + k] = 0x80000000u | (uint32_t)r.chain.size();
-        uint64_t rest = wsum[nb + k];
-        for (uint32_t q = lo; q < hi; q++) {
-            rest -= mem[q].w;
-            const ContestRec c = contest_rec(r.seed[mem[q].idx]);
-            r.chain.push_back({c.s0, c.m2, c.h2, q + 1 == hi ? 0xFFFFFFFFu : contest_t3(mem[q].w, rest), mem[q].idx});
-        }
-    }
-    r.level.clear();
-    for (uint32_t l = 0; l < bits; l++) r.level.push_back(contest_rec(level_seed(l)));
+    std::vector<TrieMember> members;
+    for (uint32_t j = 0; j < (uint32_t)r.seed.size(); j++) if (r.weight[j]) members.push_back(TrieMember{r.seed[j], j, r.weight[j]});
+    r.trie = build_trie_blob(members, r.bits);
+    r.level = trie_level_constants(r.bits);
 }
 
 uint32_t first_hop_hrw2(const rio_client_ring &r, uint64_t key) {
-    const ObjHash o = obj_hash(key);
-    uint32_t i = 1;
-    for (uint32_t l = 0; l < r.bits; l++) i = 2 * i + (contest_u(o, r.level[l].s0, r.level[l].m2, r.level[l].h2) > r.tab32[i] ? 1u : 0u);
-    const uint32_t leaf = r.tab32[i];
-    if (leaf == kNone || !(leaf & 0x80000000u)) return leaf;
-    for (uint32_t pos = leaf & 0x7FFFFFFFu;; pos++) {
-        const rio_client_ring::Chain &c = r.chain[pos];
-        if (contest_u(o, c.s0, c.m2, c.h2) <= c.t3) return c.idx;
-    }
+    return trie_walk_host(r.trie.words.data(), r.trie.bits, r.level.data(), obj_hash(key));
 }
 
 uint32_t pick(const rio_client_ring &r, uint64_t key) { return r.policy == RIO_CLIENT_POLICY_HRW2 ? first_hop_hrw2(r, key) : first_hop(r, key); }

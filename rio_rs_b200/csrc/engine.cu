@@ -8,6 +8,7 @@
 #include "../../include/rio_cuda_dev.h"
 #include "kernels.cuh"
 #include "spec.cuh"
+#include "trie_table.hpp"
 
 #include <dlfcn.h>
 
@@ -275,37 +276,13 @@ void build_tab(rio_placement *h, TabBufs &tb, const std::vector<uint8_t> *closed
         const bool lv = ni.live() && !(closed && (*closed)[j]);
         by_idx[j] = make_uint4((uint32_t)ni.seed, lv ? inv_weight(ni.weight) : 0u, (uint32_t)(ni.seed >> 32) | 1u, (uint32_t)ni.seed2);
     }
-    // ---- HRW2 table: thresholds of the binary trie over node positions, leaf words, chain records ----
-    const uint32_t bits = h->trie_bits, nb = 1u << bits;
-    struct Mem { uint64_t pos; uint32_t idx, w; };
-    std::vector<Mem> mem;
-    mem.reserve(live.size());
-    for (const Ent &e : live) mem.push_back(Mem{mix64(h->nodes[e.idx].seed ^ kSaltPos), e.idx, h->nodes[e.idx].weight});
-    std::sort(mem.begin(), mem.end(), [](const Mem &a, const Mem &b) { return a.pos != b.pos ? a.pos < b.pos : a.idx < b.idx; });
-    std::vector<uint64_t> wsum((size_t)2 * nb, 0);                 // heap of subtree weights, leaves at [nb, 2nb)
-    std::vector<uint32_t> bstart((size_t)nb + 1, 0);
-    for (const Mem &m : mem) { const uint32_t bk = bits ? (uint32_t)(m.pos >> (64 - bits)) : 0u; wsum[nb + bk] += m.w; bstart[bk + 1]++; }
-    for (uint32_t k = 0; k < nb; k++) bstart[k + 1] += bstart[k];
-    for (uint32_t i = nb - 1; i >= 1; i--) wsum[i] = wsum[2 * i] + wsum[2 * i + 1];
-    std::vector<uint32_t> tab32((size_t)2 * nb, 0);
-    for (uint32_t i = 1; i < nb; i++) tab32[i] = contest_t3(wsum[2 * i], wsum[2 * i + 1]);
-    std::vector<uint4> crec;                                       // two per chain member: the contest record, then {node index, 0, 0, 0}
-    const uint32_t off_crec = (uint32_t)((tab32.size() * 4 + 15) / 16 * 16);
-    for (uint32_t k = 0; k < nb; k++) {
-        const uint32_t lo = bstart[k], hi = bstart[k + 1];
-        if (lo == hi) { tab32[nb + k] = kNone; continue; }
-        if (hi - lo == 1) { tab32[nb + k] = mem[lo].idx; continue; }
-        tab32[nb + k] = 0x80000000u | (off_crec + (uint32_t)crec.size() * 16u);   // byte offset of the chain's first record in the blob
-        uint64_t rest = wsum[nb + k];
-        for (uint32_t q = lo; q + 1 < hi; q++) {                                  // the last member needs no record: it is always taken
-            rest -= mem[q].w;
-            const ContestRec r = contest_rec(h->nodes[mem[q].idx].seed);
-            crec.push_back(make_uint4(r.s0, r.m2, r.h2, contest_t3(mem[q].w, rest)));
-            const uint32_t next = q + 2 == hi ? mem[hi - 1].idx : 0x80000000u | (off_crec + (uint32_t)(crec.size() + 1) * 16u);
-            crec.push_back(make_uint4(mem[q].idx, next, 0, 0));
-        }
-    }
-    const uint32_t blob_bytes = std::max<uint32_t>(16u, off_crec + (uint32_t)crec.size() * 16u);
+    // ---- HRW2 table: thresholds of the binary trie over node positions, leaf words, chain records: the builder
+    // is shared with the client library (trie_table.hpp), so clients and servers walk byte-identical tables ----
+    std::vector<TrieMember> members;
+    members.reserve(live.size());
+    for (const Ent &e : live) members.push_back(TrieMember{h->nodes[e.idx].seed, e.idx, h->nodes[e.idx].weight});
+    const TrieBlob blob = build_trie_blob(members, h->trie_bits);
+    const uint32_t bits = blob.bits, nb = 1u << bits, blob_bytes = blob.blob_bytes;
     // the policy's view of every interned node (service.rs:226-231 asks is_active only: a draining node -- active, weight 0 --
     // keeps its objects) and the solver's (active and weight > 0)
     std::vector<uint8_t> state(n_total ? n_total : 1, 0);
@@ -330,20 +307,18 @@ void build_tab(rio_placement *h, TabBufs &tb, const std::vector<uint8_t> *closed
         CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&tb.stage), total * 2));
         tb.stage_cap = total * 2;
     }
-    memset(tb.stage + o_trie, 0, blob_bytes);
     memcpy(tb.stage + o_recs, recs.data(), recs.size() * sizeof(NodeRec));
     memcpy(tb.stage + o_classes, classes.data(), classes.size() * sizeof(ClassRec));
     memcpy(tb.stage + o_byidx, by_idx.data(), by_idx.size() * sizeof(uint4));
-    memcpy(tb.stage + o_trie, tab32.data(), tab32.size() * 4);
-    if (!crec.empty()) memcpy(tb.stage + o_trie + off_crec, crec.data(), crec.size() * 16);
+    memcpy(tb.stage + o_trie, blob.words.data(), blob_bytes);
     memcpy(tb.stage + o_state, state.data(), state.size());
     memcpy(tb.stage + o_live, livef.data(), livef.size() * 4);
     tb.dev.ensure(total, st);
     CUDA_TRY(cudaMemcpyAsync(tb.dev.p, tb.stage, total, cudaMemcpyHostToDevice, st));
     tb.upload_pending = true;
     unsigned char *d = tb.dev.as<unsigned char>();
-    tb.trie = TrieDev{d + o_trie, blob_bytes, off_crec, bits, (uint32_t)crec.size() / 2, {}};
-    for (uint32_t i = 1; i < 8 && i < nb; i++) tb.trie.top[i] = tab32[i];
+    tb.trie = TrieDev{d + o_trie, blob_bytes, blob.off_crec, bits, blob.n_chain, {}};
+    for (uint32_t i = 1; i < 8 && i < nb; i++) tb.trie.top[i] = blob.words[i];
     tb.tab.recs = reinterpret_cast<const NodeRec *>(d + o_recs);
     tb.tab.classes = reinterpret_cast<const ClassRec *>(d + o_classes);
     tb.tab.by_idx = reinterpret_cast<const uint4 *>(d + o_byidx);

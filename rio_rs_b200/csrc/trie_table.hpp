@@ -1,0 +1,107 @@
+// trie_table.hpp -- the HRW2 table as ONE host-side builder and ONE host-side walk, plain C++.
+//
+// Two users: engine.cu (build_tab: the blob is copied into the pinned staging area and walked on the device by k_trie.cu) and
+// client.cpp (librio_client.so: a client resolves its first hop on its own CPU by walking the very same blob).  Clients and
+// servers therefore cannot disagree about the table, and the CPU test-suite of the client library (tests/test_client_first_hop.py,
+// against the oracle) exercises the builder the GPU path depends on.
+//
+// Blob layout (all offsets in bytes, 32-bit little-endian words):
+//   [0, 4 << bits)                 thresholds T3 of the trie nodes in heap order (index 1 = root; word 0 unused)
+//   [4 << bits, 8 << bits)         leaf words, one per bucket: a node index | 0x80000000 + byte offset of the bucket's first chain
+//                                  record | kNone (no live node in the bucket)
+//   off_crec (16-byte aligned)     chain records, 32 bytes each, k-1 for a bucket of k nodes: {s0, m2, h2, T3} of the member-keyed
+//                                  contest "this member against the rest", then {this member's node index, next, 0, 0}; next = the
+//                                  LAST member's node index when only that one is left (it would always be taken), else
+//                                  0x80000000 + byte offset of the next record
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <vector>
+
+#include "spec.cuh"
+
+namespace rio {
+
+struct TrieMember {
+    uint64_t seed;     // seed(address), DESIGN.md 3.1
+    uint32_t idx;      // the index a walk returns for this member
+    uint32_t weight;   // > 0 (only live members are listed)
+};
+
+struct TrieBlob {
+    std::vector<uint32_t> words;   // the blob; words.size() * 4 == blob_bytes, a multiple of 16
+    uint32_t blob_bytes = 0;
+    uint32_t off_crec = 0;         // byte offset of the first chain record
+    uint32_t n_chain = 0;          // chain records
+    uint32_t bits = 0;
+};
+
+// Members in any order: positions and chains are ordered by (pos(seed), idx), so the table is a function of the member SET.
+inline TrieBlob build_trie_blob(const std::vector<TrieMember> &members, uint32_t bits) {
+    const uint32_t nb = 1u << bits;
+    struct Mem { uint64_t pos; uint64_t seed; uint32_t idx, w; };
+    std::vector<Mem> mem;
+    mem.reserve(members.size());
+    for (const TrieMember &m : members)
+        if (m.weight) mem.push_back(Mem{mix64(m.seed ^ kSaltPos), m.seed, m.idx, m.weight});
+    std::sort(mem.begin(), mem.end(), [](const Mem &a, const Mem &b) { return a.pos != b.pos ? a.pos < b.pos : a.idx < b.idx; });
+    std::vector<uint64_t> wsum((size_t)2 * nb, 0);                 // heap of subtree weights, leaves at [nb, 2nb)
+    std::vector<uint32_t> bstart((size_t)nb + 1, 0);
+    for (const Mem &m : mem) { const uint32_t bk = bits ? (uint32_t)(m.pos >> (64 - bits)) : 0u; wsum[nb + bk] += m.w; bstart[bk + 1]++; }
+    for (uint32_t k = 0; k < nb; k++) bstart[k + 1] += bstart[k];
+    for (uint32_t i = nb - 1; i >= 1; i--) wsum[i] = wsum[2 * i] + wsum[2 * i + 1];
+    std::vector<uint32_t> tab32((size_t)2 * nb, 0);
+    for (uint32_t i = 1; i < nb; i++) tab32[i] = contest_t3(wsum[2 * i], wsum[2 * i + 1]);
+    struct Quad { uint32_t x, y, z, w; };
+    std::vector<Quad> crec;                                        // two per chain record: the contest, then {node index, next, 0, 0}
+    const uint32_t off_crec = (uint32_t)((tab32.size() * 4 + 15) / 16 * 16);
+    for (uint32_t k = 0; k < nb; k++) {
+        const uint32_t lo = bstart[k], hi = bstart[k + 1];
+        if (lo == hi) { tab32[nb + k] = kNone; continue; }
+        if (hi - lo == 1) { tab32[nb + k] = mem[lo].idx; continue; }
+        tab32[nb + k] = 0x80000000u | (off_crec + (uint32_t)crec.size() * 16u);   // byte offset of the chain's first record in the blob
+        uint64_t rest = wsum[nb + k];
+        for (uint32_t q = lo; q + 1 < hi; q++) {                                  // the last member needs no record: it is always taken
+            rest -= mem[q].w;
+            const ContestRec r = contest_rec(mem[q].seed);
+            crec.push_back(Quad{r.s0, r.m2, r.h2, contest_t3(mem[q].w, rest)});
+            const uint32_t next = q + 2 == hi ? mem[hi - 1].idx : 0x80000000u | (off_crec + (uint32_t)(crec.size() + 1) * 16u);
+            crec.push_back(Quad{mem[q].idx, next, 0, 0});
+        }
+    }
+    TrieBlob b;
+    b.bits = bits;
+    b.off_crec = off_crec;
+    b.n_chain = (uint32_t)crec.size() / 2;
+    b.blob_bytes = std::max<uint32_t>(16u, off_crec + (uint32_t)crec.size() * 16u);
+    b.words.assign(b.blob_bytes / 4, 0u);
+    std::copy(tab32.begin(), tab32.end(), b.words.begin());
+    for (size_t q = 0; q < crec.size(); q++) {
+        uint32_t *d = b.words.data() + off_crec / 4 + q * 4;
+        d[0] = crec[q].x; d[1] = crec[q].y; d[2] = crec[q].z; d[3] = crec[q].w;
+    }
+    return b;
+}
+
+// Per-level contest constants (pseudo-node seeds c_l): spec constants, the same for every table.
+inline std::vector<ContestRec> trie_level_constants(uint32_t levels) {
+    std::vector<ContestRec> v(levels);
+    for (uint32_t l = 0; l < levels; l++) v[l] = contest_rec(level_seed(l));
+    return v;
+}
+
+// One object's walk over the blob on the host -- statement for statement what k_trie.cu's trie_leaf_index + trie_resolve_leaf do.
+inline uint32_t trie_walk_host(const uint32_t *blob, uint32_t bits, const ContestRec *level, ObjHash o) {
+    uint32_t i = 1;
+    for (uint32_t l = 0; l < bits; l++) i = 2 * i + (contest_u(o, level[l].s0, level[l].m2, level[l].h2) > blob[i] ? 1u : 0u);
+    uint32_t w = blob[i];
+    if ((int32_t)w > -2) return w;                 // node index (top bit clear) or kNone
+    for (;;) {
+        const uint32_t *p = blob + (w & 0x7FFFFFFFu) / 4;
+        if (contest_u(o, p[0], p[1], p[2]) <= p[3]) return p[4];
+        if ((int32_t)p[5] >= 0) return p[5];
+        w = p[5];
+    }
+}
+
+}  // namespace rio

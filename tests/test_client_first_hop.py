@@ -139,3 +139,26 @@ def test_first_hop_hrw2_equals_the_oracle_and_ignores_listing_order(oracle, bits
     fh.set_active_servers(addrs, w2)
     assert (fh.first_hop_batch(keys) == oracle.assign_hrw2(keys, seeds, w2, bits=bits or 12)).all()
     assert CL.FirstHop([], None, policy="hrw2").first_hop_batch(keys[:5]).tolist() == [CL.NONE] * 5
+
+
+@pytest.mark.parametrize("M,bits,weights", [(1, 12, "ones"), (2, 1, "ones"), (300, 2, "mixed"), (1024, 12, "mixed"), (1024, 10, "ones"), (3000, 14, "mixed"),
+                                            (64, 6, "huge"), (500, 3, "huge")])
+def test_shared_table_builder_walked_on_the_host_equals_the_oracle(oracle, M, bits, weights):
+    """csrc/trie_table.hpp is the ONE builder of the HRW2 table: engine.cu uploads its blob for the kernels, the client library
+    walks the same blob on the host.  Long chains (few bits, many nodes), single-member buckets, weights near 2^32 (the 128-bit
+    branch of the threshold division), dead nodes and the empty live set -- all against the oracle, which never sees a blob."""
+    from rio_rs_b200 import client as CL
+
+    addrs, seeds, w = oracle.synth_nodes(M, uniform=(weights == "ones"))
+    if weights == "huge":
+        w = w.astype(np.uint64) * np.uint64(0x0FFFFFFF) + np.uint64(7)
+        w = np.minimum(w, np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    if M > 2:
+        w[::5] = 0
+    keys = oracle.synth_keys(20000, 11)
+    fh = CL.FirstHop(addrs, w, policy="hrw2", trie_bits=bits)
+    got = fh.first_hop_batch(keys)
+    assert (got == oracle.assign_hrw2(keys, seeds, w, bits=bits)).all()
+    assert M <= 2 or not np.isin(got, np.nonzero(w == 0)[0]).any()
+    fh.set_active_servers(addrs, np.zeros(M, dtype=np.uint32))          # nobody live: every walk ends on an empty bucket
+    assert (fh.first_hop_batch(keys[:100]) == CL.NONE).all()
