@@ -279,13 +279,23 @@ rio_status rio_cuda_durable_place_batch(rio_durable *d, const char *const *types
     std::lock_guard<std::mutex> g(d->mu);
     std::vector<uint64_t> keys(n);
     std::vector<uint32_t> before(n);
-    for (size_t k = 0; k < n; k++) keys[k] = rio_cuda_object_key(types[k], strlen(types[k]), ids[k], strlen(ids[k]));
+    for (size_t k = 0; k < n; k++) {
+        if (!types[k] || !ids[k]) { t_durable_error = "null id"; return RIO_ERR_UNKNOWN; }
+        keys[k] = rio_cuda_object_key(types[k], strlen(types[k]), ids[k], strlen(ids[k]));
+    }
     rio_status st = rio_cuda_lookup_batch(d->h, keys.data(), n, before.data());
     if (st == RIO_OK) st = rio_cuda_place_batch(d->h, keys.data(), n, policy, self_idx, out_idx);
     if (st != RIO_OK) return gpu_fail(d, st);
     // the servers place_batch cleaned: recorded on some id of the batch and not active (malformed records are dropped one by one)
     std::unordered_map<uint32_t, bool> cleaned;
-    char buf[512];
+    std::string abuf;
+    // address of an interned node, whatever its length (two calls: the length, then the bytes)
+    auto address_of = [&](uint32_t j) -> bool {
+        size_t len = 0;
+        if (rio_cuda_node_address(d->h, j, nullptr, 0, &len) != RIO_OK) return false;
+        abuf.assign(len, '\0');
+        return len == 0 || rio_cuda_node_address(d->h, j, &abuf[0], len, &len) == RIO_OK;
+    };
     if (!exec(d, "BEGIN")) return fail(d, RIO_ERR_UPSTREAM, "begin");
     bool ok = true;
     for (size_t k = 0; k < n && ok; k++) {
@@ -296,15 +306,15 @@ rio_status rio_cuda_durable_place_batch(rio_durable *d, const char *const *types
         if (rio_cuda_node_state(d->h, b, &active, &weight, &malformed) != RIO_OK) { ok = false; break; }
         cleaned[b] = true;
         if (active || malformed) continue;
-        size_t len = 0;
-        if (rio_cuda_node_address(d->h, b, buf, sizeof buf, &len) != RIO_OK) { ok = false; break; }
-        ok = run(d, d->st_clean, buf, len < sizeof buf ? len : sizeof buf, nullptr, 0, nullptr, 0, 1);
+        if (!address_of(b)) { ok = false; break; }
+        ok = run(d, d->st_clean, abuf.data(), abuf.size(), nullptr, 0, nullptr, 0, 1);
     }
     for (size_t k = 0; k < n && ok; k++) {
-        if (before[k] == out_idx[k]) continue;
-        size_t len = 0;
-        if (rio_cuda_node_address(d->h, out_idx[k], buf, sizeof buf, &len) != RIO_OK) { ok = false; break; }
-        ok = run(d, d->st_upsert, types[k], strlen(types[k]), ids[k], strlen(ids[k]), buf, len < sizeof buf ? len : sizeof buf, 3);
+        // RIO_NONE: no live server to place on (the solver policies with an empty live set) -- nothing to record; a row on a
+        // server that was cleaned is already gone
+        if (before[k] == out_idx[k] || out_idx[k] == RIO_NONE) continue;
+        if (!address_of(out_idx[k])) { ok = false; break; }
+        ok = run(d, d->st_upsert, types[k], strlen(types[k]), ids[k], strlen(ids[k]), abuf.data(), abuf.size(), 3);
     }
     if (!ok || !exec(d, "COMMIT")) { const rio_status e = fail(d, RIO_ERR_UPSTREAM, "write-through of place_batch"); exec(d, "ROLLBACK"); return e; }
     return RIO_OK;
