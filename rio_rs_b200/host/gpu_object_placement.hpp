@@ -69,11 +69,14 @@ class GpuObjectPlacement {
                                   it.server_address ? it.server_address->size() : 0));
     }
     std::optional<std::string> lookup(const ObjectId &id) const {                       // mod.rs:51
-        char buf[512];
-        size_t len = 0;
-        check(rio_cuda_lookup_str(e_->h, id.struct_name.data(), id.struct_name.size(), id.object_id.data(), id.object_id.size(), buf, sizeof buf, &len));
-        if (len == (size_t)-1) return std::nullopt;
-        return std::string(buf, len < sizeof buf ? len : sizeof buf);
+        std::string buf(256, '\0');
+        for (;;) {   // the call reports the full length; an address longer than the buffer is read again into one that fits
+            size_t len = 0;
+            check(rio_cuda_lookup_str(e_->h, id.struct_name.data(), id.struct_name.size(), id.object_id.data(), id.object_id.size(), &buf[0], buf.size(), &len));
+            if (len == (size_t)-1) return std::nullopt;
+            if (len <= buf.size()) { buf.resize(len); return buf; }
+            buf.assign(len, '\0');
+        }
     }
     void clean_server(const std::string &address) const { check(rio_cuda_clean_server_str(e_->h, address.data(), address.size())); }   // mod.rs:53
     void remove(const ObjectId &id) const {                                             // mod.rs:55
@@ -93,9 +96,11 @@ class GpuObjectPlacement {
     }
     void node_set_active(uint32_t idx, bool active) const { check(rio_cuda_node_set_active(e_->h, idx, active)); }
     std::string node_address(uint32_t idx) const {
-        char buf[512]; size_t len = 0;
-        check(rio_cuda_node_address(e_->h, idx, buf, sizeof buf, &len));
-        return std::string(buf, len);
+        size_t len = 0;
+        check(rio_cuda_node_address(e_->h, idx, nullptr, 0, &len));      // the length first, then the bytes
+        std::string a(len, '\0');
+        if (len) check(rio_cuda_node_address(e_->h, idx, &a[0], a.size(), &len));
+        return a;
     }
     std::vector<uint32_t> lookup_many(const std::vector<uint64_t> &keys) const {
         std::vector<uint32_t> out(keys.size());

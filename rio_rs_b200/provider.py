@@ -58,6 +58,20 @@ def _check(L, h, st):
     raise (Upstream if st == N.RIO_ERR_UPSTREAM else Unknown)(msg)
 
 
+def _read_str(call, first=256):
+    """String results of the C ABI (`buf, cap, out_len`; out_len == (size_t)-1 is None): a per-call buffer (callers may be
+    threads sharing one provider), read again into a larger one when the call reports more bytes than it was given room for."""
+    cap = first
+    while True:
+        buf, n = C.create_string_buffer(cap), C.c_size_t(0)
+        call(buf, cap, C.byref(n))
+        if n.value == C.c_size_t(-1).value:
+            return None
+        if n.value <= cap:
+            return buf.raw[: n.value].decode()
+        cap = n.value
+
+
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -117,11 +131,7 @@ class GpuObjectPlacement:
 
     def lookup(self, object_id):  # mod.rs:51 / local.rs:42-49 -> Option<String>
         t, i = (s.encode() for s in object_id)
-        n = C.c_size_t(0)
-        self._ck(self.L.rio_cuda_lookup_str(self.h, t, len(t), i, len(i), self._buf, 512, C.byref(n)))
-        if n.value == C.c_size_t(-1).value:
-            return None
-        return self._buf.raw[: n.value].decode()
+        return _read_str(lambda buf, cap, n: self._ck(self.L.rio_cuda_lookup_str(self.h, t, len(t), i, len(i), buf, cap, n)))
 
     def clean_server(self, address):  # mod.rs:53 / local.rs:51-58
         a = address.encode()
@@ -162,9 +172,7 @@ class GpuObjectPlacement:
         return idx.value
 
     def node_address(self, idx):
-        n = C.c_size_t(0)
-        self._ck(self.L.rio_cuda_node_address(self.h, idx, self._buf, 512, C.byref(n)))
-        return self._buf.raw[: n.value].decode()
+        return _read_str(lambda buf, cap, n: self._ck(self.L.rio_cuda_node_address(self.h, idx, buf, cap, n)))
 
     def node_count(self):
         a, b = C.c_uint32(0), C.c_uint32(0)
@@ -372,13 +380,7 @@ class Resolver:
     def get_or_create_placement(self, handler_type, handler_id):
         """Same signature as the reference's per-request function (service.rs:193-197): -> address string."""
         t, i = handler_type.encode(), handler_id.encode()
-        buf = C.create_string_buffer(256)
-        n = C.c_size_t(0)
-        st = self.L.rio_cuda_resolver_resolve_str(self.r, t, len(t), i, len(i), buf, 256, C.byref(n))
-        if st != N.RIO_OK:
-            msg = self.L.rio_cuda_resolver_last_error()
-            raise (Upstream if st == N.RIO_ERR_UPSTREAM else Unknown)(msg.decode(errors="replace") if msg else "")
-        return None if n.value == C.c_size_t(-1).value else buf.raw[: n.value].decode()
+        return _read_str(lambda buf, cap, n: self._rck(self.L.rio_cuda_resolver_resolve_str(self.r, t, len(t), i, len(i), buf, cap, n)))
 
     def _rck(self, st):
         if st != N.RIO_OK:
@@ -388,10 +390,7 @@ class Resolver:
     # the trait's per-id calls, coalesced with every other caller's (mod.rs:46-55)
     def lookup(self, object_id):
         t, i = (s.encode() for s in object_id)
-        buf = C.create_string_buffer(256)
-        n = C.c_size_t(0)
-        self._rck(self.L.rio_cuda_resolver_lookup_str(self.r, t, len(t), i, len(i), buf, 256, C.byref(n)))
-        return None if n.value == C.c_size_t(-1).value else buf.raw[: n.value].decode()
+        return _read_str(lambda buf, cap, n: self._rck(self.L.rio_cuda_resolver_lookup_str(self.r, t, len(t), i, len(i), buf, cap, n)))
 
     def update(self, item):
         t, i = (s.encode() for s in item.object_id)
