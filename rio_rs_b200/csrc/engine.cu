@@ -143,6 +143,7 @@ struct BoundedState {
     bool active = false;
     uint64_t n_total_objs = 0;
     uint32_t max_rounds = 0, M = 0;
+    uint64_t live_sig = 0;                    // the live node set (indices, weights) pass 0 and the capacities were computed for
     void release(cudaStream_t st) { buf.release(st); if (h_flags) cudaFreeHost(h_flags); h_flags = nullptr; if (ev) cudaEventDestroy(ev); ev = nullptr; }
 };
 
@@ -177,6 +178,7 @@ struct rio_placement {
     // bounded-load state kept on the device between passes: [ticket | cap | global counters | thr | closed epoch | over] x node
     BoundedState bs;                          // for rio_cuda_assign_bounded_batch (host buffers)
     uint64_t tab_version = 0;
+    uint64_t live_sig = 0;                    // live_signature() of the node set the current table was built from
     unsigned long long *d_scalars = nullptr;   // S_COUNT u64 + error u32
     unsigned long long *h_scalars = nullptr;   // pinned mirror
 
@@ -253,10 +255,12 @@ void build_tab(rio_placement *h, TabBufs &tb, const std::vector<uint8_t> *closed
     const uint32_t n_total = (uint32_t)h->nodes.size();
     struct Ent { uint32_t invw, idx; };
     std::vector<Ent> live;
+    // `closed` was sized when the bounded call began; addresses interned since then (update() may record any address) are not in it
+    auto is_closed = [&](uint32_t j) { return closed && j < closed->size() && (*closed)[j]; };
     for (uint32_t j = 0; j < n_total; j++) {
         const NodeInfo &ni = h->nodes[j];
         if (!ni.live()) continue;
-        if (closed && (*closed)[j]) continue;
+        if (is_closed(j)) continue;
         live.push_back(Ent{inv_weight(ni.weight), j});
     }
     std::sort(live.begin(), live.end(), [](const Ent &a, const Ent &b) { return a.invw != b.invw ? a.invw < b.invw : a.idx < b.idx; });
@@ -273,7 +277,7 @@ void build_tab(rio_placement *h, TabBufs &tb, const std::vector<uint8_t> *closed
     std::vector<uint4> by_idx(n_total ? n_total : 1);
     for (uint32_t j = 0; j < n_total; j++) {
         const NodeInfo &ni = h->nodes[j];
-        const bool lv = ni.live() && !(closed && (*closed)[j]);
+        const bool lv = ni.live() && !is_closed(j);
         by_idx[j] = make_uint4((uint32_t)ni.seed, lv ? inv_weight(ni.weight) : 0u, (uint32_t)(ni.seed >> 32) | 1u, (uint32_t)ni.seed2);
     }
     // ---- HRW2 table: thresholds of the binary trie over node positions, leaf words, chain records: the builder
@@ -329,6 +333,14 @@ void build_tab(rio_placement *h, TabBufs &tb, const std::vector<uint8_t> *closed
     tb.live = reinterpret_cast<const uint32_t *>(d + o_live);
 }
 
+// One word that changes when the live node set or a live weight changes (interning a never-live address does not change it).
+uint64_t live_signature(const rio_placement *h) {
+    uint64_t sig = kFnvBasis;
+    for (uint32_t j = 0; j < (uint32_t)h->nodes.size(); j++)
+        if (h->nodes[j].live()) sig = mix64(sig ^ (((uint64_t)j << 32) | h->nodes[j].weight));
+    return sig;
+}
+
 void ensure_tab(rio_placement *h) {
     if (!h->tab_dirty) return;
     build_tab(h, h->tabs, nullptr);
@@ -336,6 +348,7 @@ void ensure_tab(rio_placement *h) {
     cudaStream_t st = h->stream;
     h->tab_dirty = false;
     h->tab_version++;
+    h->live_sig = live_signature(h);
     if (!h->K) return;   // hash path only: nothing else to upload, and no synchronisation
     std::vector<float> fnode((size_t)(n_total ? n_total : 1) * h->K, 0.f);
     for (uint32_t j = 0; j < n_total; j++) {
@@ -662,6 +675,7 @@ void bounded_begin(rio_placement *h, BoundedState &bs, const uint64_t *d_keys, u
     }
     bs.active = true;
     bs.n_total_objs = n_total_objs; bs.max_rounds = max_rounds; bs.M = M;
+    bs.live_sig = h->live_sig;   // of the table pass 0 ran on (every caller went through ensure_tab)
 }
 
 // Second half: wait for the check (two words in mapped memory), run the spill rounds it asks for.  Returns the passes run.
@@ -675,6 +689,10 @@ uint32_t bounded_end(rio_placement *h, BoundedState &bs, const uint64_t *d_keys,
     for (uint32_t r = 1; r < bs.max_rounds; r++) {
         const auto [any, open] = read_flags(h, bs);                  // the one collective of the pass has happened on the device
         if (!any || !open) break;
+        // A spill round re-places objects over "live minus closed" with the capacities, counters and closed set of the table pass 0
+        // ran on.  If the live set changed between _begin and _end (a join / leave / weight change by another call) those no
+        // longer describe the same cluster -- and a node that joined since has no counter slot: refuse, the caller runs the call again.
+        REQUIRE(live_signature(h) == bs.live_sig, "the live node set changed between the two halves of a bounded call: run it again");
         zero_scalar(h, S_NSEL);
         launch_select_spill(h->L(), d_keys, d_idx, n, b.thr, b.over, r, d_sel, h->d_scalars + S_NSEL, d_counters);
         std::vector<uint32_t> ce(M, 0);

@@ -93,14 +93,32 @@ class _Engine:
             msg = self.L.rio_cuda_last_error(None)
             raise (Upstream if st == N.RIO_ERR_UPSTREAM else Unknown)(msg.decode(errors="replace") if msg else "")
         self.h = h
+        self._deps = 0             # live object sets / resolvers created on this handle
+        self._finalized = False
 
-    def __del__(self):
+    # Object sets and resolvers hold raw pointers into the engine, so the handle must outlive them whatever order the interpreter
+    # finalizes things in: objects that die together in one garbage cycle (an exception traceback that captured a test's locals is
+    # enough) get their __del__ called in ARBITRARY order.  The engine is therefore destroyed by whoever goes last.
+    def _retain(self):
+        self._deps += 1
+
+    def _release(self):
+        self._deps -= 1
+        if self._deps == 0 and self._finalized:
+            self._destroy()
+
+    def _destroy(self):
         try:
             if getattr(self, "h", None):
                 self.L.rio_cuda_destroy(self.h)
                 self.h = None
         except Exception:
             pass
+
+    def __del__(self):
+        self._finalized = True
+        if getattr(self, "_deps", 0) == 0:
+            self._destroy()
 
 
 class GpuObjectPlacement:
@@ -361,13 +379,20 @@ class Resolver:
         r = N.H()
         provider._ck(self.L.rio_cuda_resolver_create(provider.h, pol, self_idx, max_batch, max_wait_us, C.byref(r)))
         self.r = r
+        self._e = provider._e
+        self._e._retain()          # the worker thread calls into the engine until the resolver is destroyed: see _Engine._retain
 
     def close(self):
         if getattr(self, "r", None):
             self.L.rio_cuda_resolver_destroy(self.r)
             self.r = None
+            self._e._release()
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def resolve(self, key):
         out = C.c_uint32(0)
@@ -429,12 +454,15 @@ class ObjectSet:
         s = N.H()
         provider._ck(self.L.rio_cuda_set_create(provider.h, capacity, C.byref(s)))
         self.s = s
+        self._e = provider._e
+        self._e._retain()          # the set points into the engine: see _Engine._retain
 
     def __del__(self):
         try:
             if getattr(self, "s", None):
                 self.L.rio_cuda_set_destroy(self.s)
                 self.s = None
+                self._e._release()
         except Exception:
             pass
 

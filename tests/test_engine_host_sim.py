@@ -64,9 +64,14 @@ def test_gpu_test_bodies_pass_on_the_engine_host_logic(hostsim_so):
     env["RIO_HOSTSIM_LIBRARY"] = hostsim_so
     env["PYTHONPATH"] = os.path.join(ROOT, "tests") + os.pathsep + env.get("PYTHONPATH", "")
     mods = [os.path.join(ROOT, "tests", m) for m in ("test_gpu_parity.py", "test_gpu_hrw2.py", "test_gpu_integration.py")]
-    r = subprocess.run([sys.executable, "-m", "pytest"] + mods + ["-m", "gpu", "-p", "hostsim_plugin", "-q", "-x", "-p", "no:cacheprovider",
-                                                                   "-k", "not test_full_size_10m_x_1024_properties"],
-                       capture_output=True, text=True, timeout=1500, env=env, cwd=ROOT)
+    cmd = [sys.executable, "-m", "pytest"] + mods + ["-m", "gpu", "-p", "hostsim_plugin", "-q", "-x", "-p", "no:cacheprovider", "-k", "not test_full_size_10m_x_1024_properties"]
+    try:
+        import pytest_timeout  # noqa: F401  (a test blocked inside a C call is only stopped by the thread method)
+
+        cmd += ["--timeout=180", "--timeout-method=thread"]
+    except ImportError:
+        pass
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
     tail = (r.stdout + r.stderr)[-3000:]
     assert r.returncode == 0, tail
     m = re.search(r"(\d+) passed", r.stdout)
@@ -88,3 +93,21 @@ def test_cpp_harnesses_on_the_engine_host_logic_under_sanitizers(tmp_path, harne
     r = subprocess.run([exe] + [str(tmp_path) if a == "TMP" else a for a in args], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "all passed" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
     assert "AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr, r.stderr[-3000:]
+
+
+def test_abi_fuzz_on_the_engine_host_logic_under_sanitizers(tmp_path):
+    """tests/cpp/abi_fuzz.cpp: random sequences of C-ABI calls with ordinary, boundary and wrong arguments (NULL buffers, indices out of
+    range, sets used in the wrong order, tiny output buffers, membership changes in the middle of bounded calls) against engine.cu under
+    ASan + UBSan; every call must answer with a status, never with a crash, and the directory must keep answering like
+    LocalObjectPlacement.  (This harness found the heap overflow in the masked-table build that
+    test_membership_touched_between_the_two_halves_of_a_bounded_call now pins.)"""
+    exe = str(tmp_path / "abi_fuzz")
+    cmd = [GXX, "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-I" + SIM, "-I" + ROOT, "-x", "c++"] + PRODUCT + DOUBLES + \
+          [os.path.join(TCPP, "abi_fuzz.cpp"), "-o", exe, "-ldl", "-lpthread"]
+    try:
+        subprocess.check_call(cmd)
+    except subprocess.CalledProcessError:
+        pytest.skip("this toolchain has no ASan/UBSan runtime")
+    for seed in (1, 6, 24, 31):
+        r = subprocess.run([exe, str(seed), "2500"], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "abi fuzz: all passed" in r.stdout, "seed %d\n" % seed + r.stdout[-1500:] + r.stderr[-4000:]

@@ -277,3 +277,36 @@ def test_bounded_calls_in_flight_on_several_sets(gp, oracle):
     with pytest.raises(gp.Unknown):
         sets[0].assign_bounded_begin(0, 5, 4, 4)   # one bounded call per set at a time
     assert sets[0].assign_bounded_end() >= 1
+
+
+def test_membership_touched_between_the_two_halves_of_a_bounded_call(gp, oracle):
+    """What may happen between _begin and _end of a bounded call on a busy provider.  (1) Another caller records a placement on a
+    never-seen address (update() may record anything, local.rs:34-36): the node table grows by a non-live entry, the spill rounds of
+    the call in flight must neither read past their closed set (found by tests/cpp/abi_fuzz.cpp: a host heap overflow in the masked
+    table build) nor change their result.  (2) A server JOINS: the capacities, counters and closed set of the call describe the old
+    cluster, so a spill round is refused loudly -- and the same call run again gives the oracle's answer for the new cluster."""
+    p = provider(gp)
+    addrs, seeds, w = oracle.synth_nodes(65)
+    p.set_nodes(addrs[:64], w[:64])
+    n = 120_000
+    s = p.new_set(n)
+    s.synth_keys(0, n, 5)
+    keys = oracle.synth_keys(n, 5)
+    widx, wcnt, wpass = oracle.assign_bounded_hrw2(keys, seeds[:64], w[:64], 101, 100, 4, threads=8)
+    assert wpass > 1                                               # the spill rounds do fire at this cap
+    s.assign_bounded_begin(0, 101, 100, 4)
+    p.update(gp.ObjectPlacementItem.new(gp.ObjectId.new("Obj", "elsewhere"), "203.0.113.7:9"))   # interns a 65th, non-live address
+    assert s.assign_bounded_end() == wpass
+    assert (s.read() == widx).all() and (s.counters()[:64] == wcnt).all()
+    s.assign_bounded_begin(0, 101, 100, 4)
+    p.node_upsert(addrs[64], int(w[64]))                           # a live node joins mid-call
+    with pytest.raises(gp.Unknown) as e:
+        s.assign_bounded_end()
+    assert "live node set changed" in str(e.value)
+    # interning order: the 64 nodes, the recorded address (not live), the joiner
+    seeds2 = np.concatenate([seeds[:64], np.array([oracle.node_seed("203.0.113.7:9")], dtype=np.uint64), seeds[64:65]])
+    w2 = np.concatenate([w[:64], np.zeros(1, dtype=np.uint32), w[64:65]])
+    assert seeds2.dtype == np.uint64 and w2.dtype == np.uint32
+    widx2, wcnt2, wpass2 = oracle.assign_bounded_hrw2(keys, seeds2, w2, 101, 100, 4, threads=8)
+    assert s.assign_bounded(0, 101, 100, 4) == wpass2
+    assert (s.read() == widx2).all() and (s.counters() == wcnt2).all()
