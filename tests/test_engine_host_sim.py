@@ -111,3 +111,18 @@ def test_abi_fuzz_on_the_engine_host_logic_under_sanitizers(tmp_path):
     for seed in (1, 6, 24, 31):
         r = subprocess.run([exe, str(seed), "2500"], capture_output=True, text=True, timeout=600)
         assert r.returncode == 0 and "abi fuzz: all passed" in r.stdout, "seed %d\n" % seed + r.stdout[-1500:] + r.stderr[-4000:]
+
+
+def test_one_handle_shared_by_many_threads_under_tsan(tmp_path):
+    """tests/cpp/abi_threads.cpp: 8 threads x random C-ABI calls on ONE handle (string calls, batched calls, membership flapping, bounded
+    calls on private sets, a shared resolver) against engine.cu under ThreadSanitizer: "re-entrant and thread-safe per handle"."""
+    exe = str(tmp_path / "abi_threads")
+    cmd = [GXX, "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-I" + SIM, "-I" + ROOT, "-x", "c++"] + PRODUCT + DOUBLES + [os.path.join(TCPP, "abi_threads.cpp"), "-o", exe, "-ldl", "-lpthread"]
+    try:
+        subprocess.check_call(cmd)
+    except subprocess.CalledProcessError:
+        pytest.skip("this toolchain has no TSan runtime")
+    env = dict(os.environ)
+    env["TSAN_OPTIONS"] = "halt_on_error=1"
+    r = subprocess.run([exe, "8", "300"], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "abi threads: all passed" in r.stdout and "ThreadSanitizer" not in r.stderr, r.stdout[-1500:] + r.stderr[-4000:]
