@@ -126,3 +126,25 @@ def test_one_handle_shared_by_many_threads_under_tsan(tmp_path):
     env["TSAN_OPTIONS"] = "halt_on_error=1"
     r = subprocess.run([exe, "8", "300"], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and "abi threads: all passed" in r.stdout and "ThreadSanitizer" not in r.stderr, r.stdout[-1500:] + r.stderr[-4000:]
+
+
+def test_durable_provider_fuzz_with_restarts(tmp_path):
+    """tests/cpp/durable_fuzz.cpp: random update / remove / clean_server / batched update / written-through place_batch / member
+    deaths / crash-and-recover sequences on the native durable provider (durable.cu over engine.cu, real libsqlite3) against a shadow
+    map with the reference's semantics; after every restart the recovered directory must hold exactly the shadow's rows."""
+    import ctypes
+
+    try:
+        ctypes.CDLL("libsqlite3.so.0")
+    except OSError:
+        pytest.skip("libsqlite3 is not installed")
+    exe = str(tmp_path / "durable_fuzz")
+    cmd = [GXX, "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-I" + SIM, "-I" + ROOT, "-x", "c++"] + PRODUCT + DOUBLES + \
+          [os.path.join(TCPP, "durable_fuzz.cpp"), "-o", exe, "-ldl", "-lpthread"]
+    try:
+        subprocess.check_call(cmd)
+    except subprocess.CalledProcessError:
+        pytest.skip("this toolchain has no ASan/UBSan runtime")
+    for seed in (1, 2, 3):
+        r = subprocess.run([exe, str(tmp_path), str(seed), "1200"], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "durable fuzz: all passed" in r.stdout, "seed %d\n" % seed + r.stdout[-1500:] + r.stderr[-4000:]
