@@ -7,6 +7,8 @@
 // (the same scalar functions the kernels use) but none of the kernels' structure -- no groups, no tiles, no staging.  A test that
 // passes here says the engine's host side hands the right tables, flags, counters and round decisions to the device; what the
 // KERNELS compute is proven on the GPU box against the oracle, never here.
+#include <sched.h>
+
 #include <algorithm>
 #include <cstring>
 #include <vector>
@@ -44,9 +46,31 @@ const ContestRec *levels() {
 }
 uint32_t walk(uint64_t key, const TrieDev &t) { return trie_walk_host(reinterpret_cast<const uint32_t *>(t.blob), t.bits, levels(), obj_hash(key)); }
 
-// the bounded-load capacity check of a pass (csrc/bounded_tail.cuh), one rank
+// The counter exchange of a pass over the ranks' windows (csrc/bounded_tail.cuh): window = slots[2][world][max_nodes]
+// then flags[world].  My counters go into slot [epoch & 1][rank] of EVERY rank's window, then my flag in every window takes the epoch
+// (release); I wait until every flag of MY window carries it (acquire) and sum my window's slots.  In this build the "peers" are other
+// handles of the same process (the stand-in IPC handle is the pointer itself), each driven by its own thread.
+void exchange(const uint32_t *local, uint32_t *const *win, uint32_t rank, uint32_t world, uint32_t M, uint32_t max_nodes, uint32_t epoch, uint32_t *out) {
+    const size_t slot_words = (size_t)2 * world * max_nodes, par = (size_t)(epoch & 1u) * world * max_nodes;
+    for (uint32_t p = 0; p < world; p++) memcpy(win[p] + par + (size_t)rank * max_nodes, local, (size_t)M * 4);
+    for (uint32_t p = 0; p < world; p++) __atomic_store_n(win[p] + slot_words + rank, epoch, __ATOMIC_RELEASE);
+    for (uint32_t r = 0; r < world; r++)
+        while ((int32_t)(__atomic_load_n(win[rank] + slot_words + r, __ATOMIC_ACQUIRE) - epoch) < 0) sched_yield();
+    for (uint32_t j = 0; j < M; j++) {
+        uint32_t sum = 0;
+        for (uint32_t r = 0; r < world; r++) sum += win[rank][par + (size_t)r * max_nodes + j];
+        out[j] = sum;
+    }
+}
+
+// the tail of a bounded-load pass (csrc/bounded_tail.cuh): exchange (world > 1), then the capacity check on the
+// GLOBAL counters
 void capacity_check(const BoundedTail &b, const uint32_t *local) {
     uint32_t any = 0, open = 0;
+    if (b.world > 1) {
+        exchange(local, b.peers.win, b.rank, b.world, b.M, b.max_nodes, b.xchg_epoch, b.glob);
+        local = b.glob;
+    }
     for (uint32_t j = 0; j < b.M; j++) {
         const uint32_t c = local[j], cp = b.cap[j], ce = b.closed_epoch[j];
         const bool live = b.state[j] & kNodeLive;
@@ -184,11 +208,11 @@ void launch_select_spill(const Launch &L, const uint64_t *keys, const uint32_t *
     count(L);
 }
 void launch_exchange_check(const Launch &L, const uint32_t *local, const BoundedTail &b) {
-    capacity_check(b, local);   // world == 1 in this build: there is no peer to exchange with
+    capacity_check(b, local);
     count(L);
 }
-void launch_exchange_p2p(const Launch &L, const uint32_t *local, uint32_t *const *, uint32_t, uint32_t, uint32_t M, uint32_t, uint32_t, uint32_t *out) {
-    if (out != local) memcpy(out, local, (size_t)M * 4);
+void launch_exchange_p2p(const Launch &L, const uint32_t *local, uint32_t *const *win, uint32_t rank, uint32_t world, uint32_t M, uint32_t max_nodes, uint32_t epoch, uint32_t *out) {
+    exchange(local, win, rank, world, M, max_nodes, epoch, out);
     count(L);
 }
 void launch_sum_gathered(const Launch &L, const uint32_t *g, uint32_t world, uint32_t M, uint32_t *out) {

@@ -148,3 +148,14 @@ def test_durable_provider_fuzz_with_restarts(tmp_path):
     for seed in (1, 2, 3):
         r = subprocess.run([exe, str(tmp_path), str(seed), "1200"], capture_output=True, text=True, timeout=600)
         assert r.returncode == 0 and "durable fuzz: all passed" in r.stdout, "seed %d\n" % seed + r.stdout[-1500:] + r.stderr[-4000:]
+
+
+@pytest.mark.parametrize("world,solver", [(2, "hrw2"), (4, "hrw"), (8, "hrw2"), (8, "hrw")])
+def test_multi_rank_host_path_in_one_process(hostsim_so, world, solver):
+    """tests/hostsim_multirank.py: `world` ranks of the engine as threads of one process, windows attached through the same
+    rio_cuda_comm_ipc_* calls a multi-process run uses: bounded calls whose spill rounds fire, three calls in flight, leave / join,
+    global counters -- every rank's shard equal to the oracle on the GLOBAL key set, up to the 8 ranks no GPU box was free for."""
+    env = dict(os.environ)
+    env["RIO_HOSTSIM_LIBRARY"] = hostsim_so
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "hostsim_multirank.py"), str(world), solver], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert r.returncode == 0 and "multirank ok" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
