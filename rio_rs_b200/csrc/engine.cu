@@ -263,7 +263,29 @@ void build_tab(rio_placement *h, TabBufs &tb, const std::vector<uint8_t> *closed
         if (is_closed(j)) continue;
         live.push_back(Ent{inv_weight(ni.weight), j});
     }
-    std::sort(live.begin(), live.end(), [](const Ent &a, const Ent &b) { return a.invw != b.invw ? a.invw < b.invw : a.idx < b.idx; });
+    // Order by (inverse weight, node index).  `live` is in index order already, so this is a STABLE grouping by inverse weight: with
+    // the few weight classes real clusters have (<= 64 distinct values) it is two linear passes instead of a sort; otherwise sort.
+    {
+        std::vector<uint32_t> classes_seen;
+        bool few = true;
+        for (const Ent &e : live) {
+            if (std::find(classes_seen.begin(), classes_seen.end(), e.invw) != classes_seen.end()) continue;
+            if (classes_seen.size() == 64) { few = false; break; }
+            classes_seen.push_back(e.invw);
+        }
+        if (few) {
+            std::sort(classes_seen.begin(), classes_seen.end());
+            std::vector<uint32_t> start(classes_seen.size() + 1, 0);
+            auto cls = [&](uint32_t invw) { return (size_t)(std::lower_bound(classes_seen.begin(), classes_seen.end(), invw) - classes_seen.begin()); };
+            for (const Ent &e : live) start[cls(e.invw) + 1]++;
+            for (size_t c = 0; c < classes_seen.size(); c++) start[c + 1] += start[c];
+            std::vector<Ent> grouped(live.size());
+            for (const Ent &e : live) grouped[start[cls(e.invw)]++] = e;
+            live.swap(grouped);
+        } else {
+            std::sort(live.begin(), live.end(), [](const Ent &a, const Ent &b) { return a.invw != b.invw ? a.invw < b.invw : a.idx < b.idx; });
+        }
+    }
     std::vector<NodeRec> recs(live.size() ? live.size() : 1);
     std::vector<ClassRec> classes;
     for (size_t q = 0; q < live.size(); q++) {

@@ -36,22 +36,55 @@ struct TrieBlob {
     uint32_t bits = 0;
 };
 
+// T3 of a contest (spec.cuh contest_t3) for the common case "both weights and their sum below 2^32": floor(2^31 wl / (wl + wr)) by one
+// double-precision division and an exact integer correction instead of a 64-bit hardware division (~25-40 ns each on server CPUs; a
+// table rebuild does one per trie node with two non-empty subtrees and one per chain record).  q0 is within 1 of the true quotient (the
+// operands are exact in a double, the quotient <= 2^31 has 22 bits of slack), the two loops make it exact; everything else falls back
+// to the reference form.  tests/test_client_first_hop.py compares both forms on edge and random operands.
+inline uint32_t contest_t3_fast(uint64_t wl, uint64_t wr) {
+    if (wl == 0) return 0u;
+    if (wr == 0) return 0xFFFFFFFFu;
+    const uint64_t s = wl + wr;
+    if (s >= (1ull << 32)) return contest_t3(wl, wr);
+    const uint64_t num = wl << 31;                                  // < 2^63
+    uint64_t q = (uint64_t)((double)num / (double)s);
+    while (q * s > num) q--;                                        // q * s <= 2^31 * 2^32: no overflow
+    while ((q + 1) * s <= num) q++;
+    return q ? (uint32_t)(2 * q - 1) : 0u;
+}
+
 // Members in any order: positions and chains are ordered by (pos(seed), idx), so the table is a function of the member SET.
 inline TrieBlob build_trie_blob(const std::vector<TrieMember> &members, uint32_t bits) {
     const uint32_t nb = 1u << bits;
     struct Mem { uint64_t pos; uint64_t seed; uint32_t idx, w; };
-    std::vector<Mem> mem;
-    mem.reserve(members.size());
-    for (const TrieMember &m : members)
-        if (m.weight) mem.push_back(Mem{mix64(m.seed ^ kSaltPos), m.seed, m.idx, m.weight});
-    std::sort(mem.begin(), mem.end(), [](const Mem &a, const Mem &b) { return a.pos != b.pos ? a.pos < b.pos : a.idx < b.idx; });
-    std::vector<uint64_t> wsum((size_t)2 * nb, 0);                 // heap of subtree weights, leaves at [nb, 2nb)
+    // Order by (pos, idx) without a full sort: the bucket is the top `bits` bits of pos, so members are dropped into their buckets by
+    // counting (two linear passes) and only the few buckets that hold more than one member are sorted.
     std::vector<uint32_t> bstart((size_t)nb + 1, 0);
-    for (const Mem &m : mem) { const uint32_t bk = bits ? (uint32_t)(m.pos >> (64 - bits)) : 0u; wsum[nb + bk] += m.w; bstart[bk + 1]++; }
+    std::vector<Mem> all;
+    all.reserve(members.size());
+    for (const TrieMember &m : members) {
+        if (!m.weight) continue;
+        const uint64_t pos = mix64(m.seed ^ kSaltPos);
+        all.push_back(Mem{pos, m.seed, m.idx, m.weight});
+        bstart[(bits ? (uint32_t)(pos >> (64 - bits)) : 0u) + 1]++;
+    }
     for (uint32_t k = 0; k < nb; k++) bstart[k + 1] += bstart[k];
+    std::vector<Mem> mem(all.size());
+    {
+        std::vector<uint32_t> fill(bstart.begin(), bstart.end() - 1);
+        for (const Mem &m : all) mem[fill[bits ? (uint32_t)(m.pos >> (64 - bits)) : 0u]++] = m;
+    }
+    std::vector<uint64_t> wsum((size_t)2 * nb, 0);                 // heap of subtree weights, leaves at [nb, 2nb)
+    for (uint32_t k = 0; k < nb; k++) {
+        const uint32_t lo = bstart[k], hi = bstart[k + 1];
+        if (hi - lo > 1) std::sort(mem.begin() + lo, mem.begin() + hi, [](const Mem &a, const Mem &b) { return a.pos != b.pos ? a.pos < b.pos : a.idx < b.idx; });
+        uint64_t sum = 0;
+        for (uint32_t q = lo; q < hi; q++) sum += mem[q].w;
+        wsum[nb + k] = sum;
+    }
     for (uint32_t i = nb - 1; i >= 1; i--) wsum[i] = wsum[2 * i] + wsum[2 * i + 1];
     std::vector<uint32_t> tab32((size_t)2 * nb, 0);
-    for (uint32_t i = 1; i < nb; i++) tab32[i] = contest_t3(wsum[2 * i], wsum[2 * i + 1]);
+    for (uint32_t i = 1; i < nb; i++) tab32[i] = contest_t3_fast(wsum[2 * i], wsum[2 * i + 1]);
     struct Quad { uint32_t x, y, z, w; };
     std::vector<Quad> crec;                                        // two per chain record: the contest, then {node index, next, 0, 0}
     const uint32_t off_crec = (uint32_t)((tab32.size() * 4 + 15) / 16 * 16);
@@ -64,7 +97,7 @@ inline TrieBlob build_trie_blob(const std::vector<TrieMember> &members, uint32_t
         for (uint32_t q = lo; q + 1 < hi; q++) {                                  // the last member needs no record: it is always taken
             rest -= mem[q].w;
             const ContestRec r = contest_rec(mem[q].seed);
-            crec.push_back(Quad{r.s0, r.m2, r.h2, contest_t3(mem[q].w, rest)});
+            crec.push_back(Quad{r.s0, r.m2, r.h2, contest_t3_fast(mem[q].w, rest)});
             const uint32_t next = q + 2 == hi ? mem[hi - 1].idx : 0x80000000u | (off_crec + (uint32_t)(crec.size() + 1) * 16u);
             crec.push_back(Quad{mem[q].idx, next, 0, 0});
         }

@@ -162,3 +162,19 @@ def test_shared_table_builder_walked_on_the_host_equals_the_oracle(oracle, M, bi
     assert M <= 2 or not np.isin(got, np.nonzero(w == 0)[0]).any()
     fh.set_active_servers(addrs, np.zeros(M, dtype=np.uint32))          # nobody live: every walk ends on an empty bucket
     assert (fh.first_hop_batch(keys[:100]) == CL.NONE).all()
+
+
+def test_table_builder_shortcuts_equal_the_plain_statement(tmp_path):
+    """tests/cpp/trie_table_selftest.cpp: the shipped builder (no full sort, no 64-bit divisions: a rebuild is on the critical path of
+    every membership event) against the layout of DESIGN.md 3.8 / 4.1 read literally -- byte for byte on 324 member sets, and the fast
+    threshold division against the reference one on 4 M operand pairs (edges, random, next to exact multiples)."""
+    import shutil
+    import subprocess
+
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+    if not gxx:
+        pytest.skip("no host C++ compiler")
+    exe = str(tmp_path / "selftest")
+    subprocess.check_call([gxx, "-std=c++17", "-O2", "-Wall", "-Wextra", "-Werror", os.path.join(ROOT, "tests", "cpp", "trie_table_selftest.cpp"), "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "all passed" in r.stdout, r.stdout + r.stderr
