@@ -16,6 +16,7 @@
 #pragma once
 #include <algorithm>
 #include <cstdint>
+#include <memory>
 #include <vector>
 
 #include "spec.cuh"
@@ -69,49 +70,47 @@ inline TrieBlob build_trie_blob(const std::vector<TrieMember> &members, uint32_t
         bstart[(bits ? (uint32_t)(pos >> (64 - bits)) : 0u) + 1]++;
     }
     for (uint32_t k = 0; k < nb; k++) bstart[k + 1] += bstart[k];
-    std::vector<Mem> mem(all.size());
+    std::unique_ptr<Mem[]> mem(new Mem[all.size() ? all.size() : 1]);     // every element is written below
     {
         std::vector<uint32_t> fill(bstart.begin(), bstart.end() - 1);
         for (const Mem &m : all) mem[fill[bits ? (uint32_t)(m.pos >> (64 - bits)) : 0u]++] = m;
     }
     std::vector<uint64_t> wsum((size_t)2 * nb, 0);                 // heap of subtree weights, leaves at [nb, 2nb)
+    uint32_t n_rec = 0;                                            // chain records: k-1 for a bucket of k >= 2 members
     for (uint32_t k = 0; k < nb; k++) {
         const uint32_t lo = bstart[k], hi = bstart[k + 1];
-        if (hi - lo > 1) std::sort(mem.begin() + lo, mem.begin() + hi, [](const Mem &a, const Mem &b) { return a.pos != b.pos ? a.pos < b.pos : a.idx < b.idx; });
+        if (hi - lo > 1) {
+            std::sort(mem.get() + lo, mem.get() + hi, [](const Mem &a, const Mem &b) { return a.pos != b.pos ? a.pos < b.pos : a.idx < b.idx; });
+            n_rec += hi - lo - 1;
+        }
         uint64_t sum = 0;
         for (uint32_t q = lo; q < hi; q++) sum += mem[q].w;
         wsum[nb + k] = sum;
     }
     for (uint32_t i = nb - 1; i >= 1; i--) wsum[i] = wsum[2 * i] + wsum[2 * i + 1];
-    std::vector<uint32_t> tab32((size_t)2 * nb, 0);
-    for (uint32_t i = 1; i < nb; i++) tab32[i] = contest_t3_fast(wsum[2 * i], wsum[2 * i + 1]);
-    struct Quad { uint32_t x, y, z, w; };
-    std::vector<Quad> crec;                                        // two per chain record: the contest, then {node index, next, 0, 0}
-    const uint32_t off_crec = (uint32_t)((tab32.size() * 4 + 15) / 16 * 16);
-    for (uint32_t k = 0; k < nb; k++) {
-        const uint32_t lo = bstart[k], hi = bstart[k + 1];
-        if (lo == hi) { tab32[nb + k] = kNone; continue; }
-        if (hi - lo == 1) { tab32[nb + k] = mem[lo].idx; continue; }
-        tab32[nb + k] = 0x80000000u | (off_crec + (uint32_t)crec.size() * 16u);   // byte offset of the chain's first record in the blob
-        uint64_t rest = wsum[nb + k];
-        for (uint32_t q = lo; q + 1 < hi; q++) {                                  // the last member needs no record: it is always taken
-            rest -= mem[q].w;
-            const ContestRec r = contest_rec(mem[q].seed);
-            crec.push_back(Quad{r.s0, r.m2, r.h2, contest_t3_fast(mem[q].w, rest)});
-            const uint32_t next = q + 2 == hi ? mem[hi - 1].idx : 0x80000000u | (off_crec + (uint32_t)(crec.size() + 1) * 16u);
-            crec.push_back(Quad{mem[q].idx, next, 0, 0});
-        }
-    }
     TrieBlob b;
     b.bits = bits;
-    b.off_crec = off_crec;
-    b.n_chain = (uint32_t)crec.size() / 2;
-    b.blob_bytes = std::max<uint32_t>(16u, off_crec + (uint32_t)crec.size() * 16u);
-    b.words.assign(b.blob_bytes / 4, 0u);
-    std::copy(tab32.begin(), tab32.end(), b.words.begin());
-    for (size_t q = 0; q < crec.size(); q++) {
-        uint32_t *d = b.words.data() + off_crec / 4 + q * 4;
-        d[0] = crec[q].x; d[1] = crec[q].y; d[2] = crec[q].z; d[3] = crec[q].w;
+    b.off_crec = (uint32_t)(((size_t)2 * nb * 4 + 15) / 16 * 16);
+    b.n_chain = n_rec;
+    b.blob_bytes = std::max<uint32_t>(16u, b.off_crec + n_rec * 32u);
+    b.words.assign(b.blob_bytes / 4, 0u);                          // thresholds, leaves and records are written in place
+    uint32_t *w32 = b.words.data();
+    for (uint32_t i = 1; i < nb; i++) w32[i] = contest_t3_fast(wsum[2 * i], wsum[2 * i + 1]);
+    uint32_t rec_off = b.off_crec;                                 // byte offset of the next chain record
+    for (uint32_t k = 0; k < nb; k++) {
+        const uint32_t lo = bstart[k], hi = bstart[k + 1];
+        if (lo == hi) { w32[nb + k] = kNone; continue; }
+        if (hi - lo == 1) { w32[nb + k] = mem[lo].idx; continue; }
+        w32[nb + k] = 0x80000000u | rec_off;                       // the chain's first record
+        uint64_t rest = wsum[nb + k];
+        for (uint32_t q = lo; q + 1 < hi; q++, rec_off += 32u) {   // the last member needs no record: it is always taken
+            rest -= mem[q].w;
+            const ContestRec r = contest_rec(mem[q].seed);
+            uint32_t *d = w32 + rec_off / 4;
+            d[0] = r.s0; d[1] = r.m2; d[2] = r.h2; d[3] = contest_t3_fast(mem[q].w, rest);
+            d[4] = mem[q].idx;
+            d[5] = q + 2 == hi ? mem[hi - 1].idx : 0x80000000u | (rec_off + 32u);
+        }
     }
     return b;
 }
