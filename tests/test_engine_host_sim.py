@@ -55,6 +55,8 @@ def test_the_doubles_cover_every_launcher_and_nothing_in_the_product_knows_them(
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 assert "hostsim" not in open(os.path.join(dirpath, f), errors="replace").read(), f
+    for f in ("bench.py", "__graft_entry__.py", os.path.join("include", "rio_cuda.h"), os.path.join("include", "rio_cuda_dev.h")):
+        assert "hostsim" not in open(os.path.join(ROOT, f)).read(), f     # neither the bench nor the driver's entry points can reach it
 
 
 def test_gpu_test_bodies_pass_on_the_engine_host_logic(hostsim_so):
